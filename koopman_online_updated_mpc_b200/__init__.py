@@ -1,0 +1,21 @@
+"""koopman_online_updated_mpc_b200 -- B200-native batched closed-loop Koopman-MPC hot path.
+
+Python here is host glue only: every operator calls hand-written sm_100a CUDA kernels through
+the C ABI of libkmpc.so (include/kmpc.h).  There is no CPU fallback.  The module layout mirrors
+the reference's call sites (duffing.py / vanderpol.py / duffing_RBF.py / Tank_System.m):
+
+    lift.Encoder(x), lift.rbf(x, cx)          stage 1  (duffing.py:764, duffing_RBF.py:20-23)
+    edmd.edmd(PHIX, PHIY, U, X)               stage 2  (duffing.py:167-177)
+    rls.rls_update(state, z, u, y, x_next)    stage 3  (duffing.py:927-984)
+    mpc.mpc_first_move(A, B, C, z0, r, lb, ub) stage 4 (duffing.py:776-778, Tank_System.m:188)
+    plant.f_update(x, u, params)              plant    (duffing.py:250-261)
+    closed_loop.ClosedLoop(...).run(T)        fused scenario steps (duffing.py:823-992)
+"""
+from . import closed_loop, distributed, edmd, lift, mpc, plant, rls, weights  # noqa: F401
+from ._lib import KmpcError, launch_count, lib  # noqa: F401
+from .build import build  # noqa: F401
+from .closed_loop import ClosedLoop, LoopSpec, duffing_spec, rbf_spec, tank_spec, vanderpol_spec  # noqa: F401
+from .lift import Encoder, rbf  # noqa: F401
+from .rls import RLSState, rls_update  # noqa: F401
+
+__version__ = "0.1.0"

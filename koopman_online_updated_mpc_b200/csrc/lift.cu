@@ -1,0 +1,255 @@
+// lift.cu -- theta_E encoder MLP (fp64, CUDA-core register-tiled batched GEMM chain).
+//
+// Reference: duffing.py:21-29 (`nn.Sequential(Linear(2,100), ReLU, Linear(100,100), ReLU,
+// Linear(100,100), ReLU, Linear(100,8))`), Encoder_Tank.m:3-5 (3 layers, nz = 10).
+//
+// Layout: one CTA lifts a tile of kTileS = 32 scenarios through ALL layers; activations stay in
+// shared memory, k-major ([k][scenario]) so a thread's 4 consecutive scenarios are one 32-byte
+// read that is broadcast to the 4 lanes sharing the row group.  Weights are stored transposed and
+// padded ([in][out_pad], out_pad multiple of 4) in global memory and read through L1 (all CTAs
+// read the same 170 KB, so they are L1/L2 hits).  Each thread owns a 4 (scenarios) x 4 (outputs)
+// register tile: 16 DFMA per 4 shared + 4 global 8-byte loads.
+#include <vector>
+
+#include "common.cuh"
+
+namespace kmpc {
+
+constexpr int kTileS = 32;         // scenarios per CTA
+constexpr int kEncWarps = 7;       // 7 warps x 4 column groups x 4 outputs = 112 outputs per pass
+constexpr int kEncThreads = kEncWarps * 32;
+
+struct EncParams {
+  int n_layers;
+  int dims[KMPC_MAX_LAYERS + 1];
+  int pad[KMPC_MAX_LAYERS + 1];
+  const double* wt[KMPC_MAX_LAYERS];
+  const double* b[KMPC_MAX_LAYERS];
+  const double* z0;
+};
+
+__global__ void __launch_bounds__(kEncThreads)
+encoder_kernel(EncParams p, const double* __restrict__ x, double* __restrict__ z, int64_t S,
+               int lift_mode, int out_dim) {
+  extern __shared__ double smem[];
+  double* act_in = smem;
+  double* act_out = smem + KMPC_MAX_WIDTH * kTileS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * kTileS;
+  const int n = p.dims[0];
+  for (int e = tid; e < kTileS * n; e += kEncThreads) {
+    const int r = e / n, k = e - r * n;
+    const double v = (row0 + r < S) ? x[(row0 + r) * n + k] : 0.0;
+    act_in[k * kTileS + r] = v;
+    if (lift_mode == KMPC_LIFT_STACK && row0 + r < S) z[(row0 + r) * out_dim + k] = v;
+  }
+  __syncthreads();
+  const int rg = lane & 7, cgl = lane >> 3;
+  const int off = (lift_mode == KMPC_LIFT_STACK) ? n : 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const int in = p.dims[l], outp = p.pad[l + 1], out = p.dims[l + 1];
+    const int ncg = outp >> 2;
+    const bool last = (l == p.n_layers - 1);
+    const double* __restrict__ wt = p.wt[l];
+    const double* __restrict__ bias = p.b[l];
+    for (int cg0 = 0; cg0 < ncg; cg0 += kEncWarps * 4) {
+      const int cg = cg0 + warp * 4 + cgl;
+      if (cg < ncg) {
+        double acc[4][4];
+        {
+          const double2 b01 = __ldg(reinterpret_cast<const double2*>(bias + 4 * cg));
+          const double2 b23 = __ldg(reinterpret_cast<const double2*>(bias + 4 * cg + 2));
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            acc[r][0] = b01.x;
+            acc[r][1] = b01.y;
+            acc[r][2] = b23.x;
+            acc[r][3] = b23.y;
+          }
+        }
+        const double* hp = act_in + 4 * rg;
+        const double* wp = wt + 4 * cg;
+#pragma unroll 4
+        for (int k = 0; k < in; ++k) {
+          const double2 h01 = *reinterpret_cast<const double2*>(hp + k * kTileS);
+          const double2 h23 = *reinterpret_cast<const double2*>(hp + k * kTileS + 2);
+          const double2 w01 = __ldg(reinterpret_cast<const double2*>(wp + (size_t)k * outp));
+          const double2 w23 = __ldg(reinterpret_cast<const double2*>(wp + (size_t)k * outp + 2));
+          const double h[4] = {h01.x, h01.y, h23.x, h23.y};
+          const double w[4] = {w01.x, w01.y, w23.x, w23.y};
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = fma(h[r], w[c], acc[r][c]);
+        }
+        if (!last) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            double2 o01, o23;
+            o01.x = fmax(acc[0][c], 0.0);
+            o01.y = fmax(acc[1][c], 0.0);
+            o23.x = fmax(acc[2][c], 0.0);
+            o23.y = fmax(acc[3][c], 0.0);
+            double* op = act_out + (4 * cg + c) * kTileS + 4 * rg;
+            *reinterpret_cast<double2*>(op) = o01;
+            *reinterpret_cast<double2*>(op + 2) = o23;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int64_t row = row0 + 4 * rg + r;
+            if (row < S) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int col = 4 * cg + c;
+                if (col < out) {
+                  double v = acc[r][c];
+                  if (lift_mode != KMPC_LIFT_RAW) v -= p.z0[col];
+                  z[row * out_dim + off + col] = v;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    double* t = act_in;
+    act_in = act_out;
+    act_out = t;
+  }
+}
+
+}  // namespace kmpc
+
+using namespace kmpc;
+
+struct kmpc_encoder {
+  EncParams p;
+  std::vector<double*> owned;
+  double* d_z0 = nullptr;
+  // L2-resident lift workspace for kmpc_gram_from_snapshots (allocated on first use)
+  double* d_ws = nullptr;
+  int64_t ws_rows = 0;
+};
+
+static int launch_encoder(const kmpc_encoder* enc, const double* x, double* z, int64_t S,
+                          int lift_mode, cudaStream_t st) {
+  const int smem = 2 * KMPC_MAX_WIDTH * kTileS * (int)sizeof(double);
+  KMPC_CUDA(ensure_smem(encoder_kernel, smem));
+  const int64_t tiles = (S + kTileS - 1) / kTileS;
+  if (tiles > 0x7fffffff) return KMPC_ERR_ARG;
+  const int out_dim = kmpc_encoder_out_dim(enc, lift_mode);
+  encoder_kernel<<<(unsigned)tiles, kEncThreads, smem, st>>>(enc->p, x, z, S, lift_mode, out_dim);
+  KMPC_AFTER_LAUNCH();
+  return KMPC_OK;
+}
+
+extern "C" {
+
+int kmpc_encoder_create(kmpc_encoder** out, const double* const* W, const double* const* b,
+                        const int* dims, int n_layers, void* stream) {
+  if (!out || !W || !b || !dims || n_layers < 1 || n_layers > KMPC_MAX_LAYERS) return KMPC_ERR_ARG;
+  for (int l = 0; l <= n_layers; ++l)
+    if (dims[l] < 1 || dims[l] > KMPC_MAX_WIDTH) return KMPC_ERR_ARG;
+  if (dims[0] > 4) return KMPC_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  kmpc_encoder* enc = new kmpc_encoder();
+  enc->p.n_layers = n_layers;
+  for (int l = 0; l <= n_layers; ++l) {
+    enc->p.dims[l] = dims[l];
+    enc->p.pad[l] = (dims[l] + 3) & ~3;
+  }
+  auto fail = [&](int code) {
+    kmpc_encoder_destroy(enc);
+    return code;
+  };
+  for (int l = 0; l < n_layers; ++l) {
+    const int in = dims[l], o = dims[l + 1], op = enc->p.pad[l + 1];
+    std::vector<double> wt((size_t)in * op, 0.0), bp(op, 0.0);
+    for (int i = 0; i < o; ++i) {
+      bp[i] = b[l][i];
+      for (int k = 0; k < in; ++k) wt[(size_t)k * op + i] = W[l][(size_t)i * in + k];
+    }
+    double *dw = nullptr, *db = nullptr;
+    if (cudaMalloc(&dw, wt.size() * sizeof(double)) != cudaSuccess) return fail(KMPC_ERR_ALLOC);
+    enc->owned.push_back(dw);
+    if (cudaMalloc(&db, bp.size() * sizeof(double)) != cudaSuccess) return fail(KMPC_ERR_ALLOC);
+    enc->owned.push_back(db);
+    // pageable-source async copies complete w.r.t. the host before returning
+    if (cudaMemcpyAsync(dw, wt.data(), wt.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(db, bp.data(), bp.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess)
+      return fail(KMPC_ERR_CUDA);
+    enc->p.wt[l] = dw;
+    enc->p.b[l] = db;
+  }
+  // theta(0) for the OFFSET / STACK lift modes (Koopman_update.m:67)
+  double* scratch = nullptr;
+  if (cudaMalloc(&scratch, (4 + KMPC_MAX_WIDTH) * sizeof(double)) != cudaSuccess) return fail(KMPC_ERR_ALLOC);
+  enc->owned.push_back(scratch);
+  enc->d_z0 = scratch + 4;
+  enc->p.z0 = enc->d_z0;
+  if (cudaMemsetAsync(scratch, 0, (4 + KMPC_MAX_WIDTH) * sizeof(double), st) != cudaSuccess)
+    return fail(KMPC_ERR_CUDA);
+  int rc = launch_encoder(enc, scratch, enc->d_z0, 1, KMPC_LIFT_RAW, st);
+  if (rc != KMPC_OK) return fail(rc);
+  if (cudaStreamSynchronize(st) != cudaSuccess) return fail(KMPC_ERR_CUDA);
+  *out = enc;
+  return KMPC_OK;
+}
+
+int kmpc_encoder_destroy(kmpc_encoder* enc) {
+  if (!enc) return KMPC_OK;
+  for (double* p : enc->owned) cudaFree(p);
+  if (enc->d_ws) cudaFree(enc->d_ws);
+  delete enc;
+  return KMPC_OK;
+}
+
+int kmpc_encoder_out_dim(const kmpc_encoder* enc, int lift_mode) {
+  if (!enc) return KMPC_ERR_ARG;
+  const int nz = enc->p.dims[enc->p.n_layers];
+  return lift_mode == KMPC_LIFT_STACK ? nz + enc->p.dims[0] : nz;
+}
+
+int kmpc_encode(const kmpc_encoder* enc, const double* x, double* z, int64_t S, int lift_mode,
+                void* stream) {
+  if (!enc || !x || !z || S < 0) return KMPC_ERR_ARG;
+  if (lift_mode < KMPC_LIFT_RAW || lift_mode > KMPC_LIFT_STACK) return KMPC_ERR_ARG;
+  if (S == 0) return KMPC_OK;
+  return launch_encoder(enc, x, z, S, lift_mode, as_stream(stream));
+}
+
+// fused lift + Gram: lifts chunks of snapshots into an L2-sized workspace owned by the encoder
+// handle and accumulates the Gram pack from it, so PHIX / PHIY never round-trip HBM in full.
+int kmpc_gram_from_snapshots(const kmpc_encoder* enc_c, int lift_mode, const double* x,
+                             const double* y, const double* u, int64_t M, double* pack,
+                             void* stream) {
+  if (!enc_c || !x || !y || !u || !pack || M < 0) return KMPC_ERR_ARG;
+  kmpc_encoder* enc = const_cast<kmpc_encoder*>(enc_c);
+  const int nzo = kmpc_encoder_out_dim(enc, lift_mode);
+  const int n = enc->p.dims[0];
+  const int64_t chunk = 1 << 18;  // 262144 snapshots: 2 * chunk * nz * 8 B = 32 MiB at nz = 8
+  if (!enc->d_ws || enc->ws_rows < chunk) {
+    if (enc->d_ws) cudaFree(enc->d_ws);
+    enc->d_ws = nullptr;
+    if (cudaMalloc(&enc->d_ws, (size_t)2 * chunk * (KMPC_MAX_NZ + 4) * sizeof(double)) != cudaSuccess)
+      return KMPC_ERR_ALLOC;
+    enc->ws_rows = chunk;
+  }
+  double* px = enc->d_ws;
+  double* py = enc->d_ws + (size_t)chunk * (KMPC_MAX_NZ + 4);
+  if (nzo > KMPC_MAX_NZ) return KMPC_ERR_UNSUPPORTED;
+  for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+    const int64_t mc = (M - m0 < chunk) ? (M - m0) : chunk;
+    int rc = launch_encoder(enc, x + m0 * n, px, mc, lift_mode, as_stream(stream));
+    if (rc != KMPC_OK) return rc;
+    rc = launch_encoder(enc, y + m0 * n, py, mc, lift_mode, as_stream(stream));
+    if (rc != KMPC_OK) return rc;
+    rc = kmpc_gram_accumulate(px, py, u + m0, x + m0 * n, mc, nzo, n, pack, stream);
+    if (rc != KMPC_OK) return rc;
+  }
+  return KMPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+// loopbody.cuh -- per-scenario bodies of the fused closed-loop kernels (one warp per scenario).
+// Written with the percase.cuh lane-loop macros so tests/hostemu can run the identical code
+// sequentially on the host.  See closed_loop.cu for the kernels and the step schedule.
+#pragma once
+#include "percase.cuh"
+
+namespace kmpc {
+
+struct LoopDev {  // passed by value to the kernels
+  kmpc_loop_config c;
+  kmpc_loop_buffers b;
+  double* z_next;  // ctx-owned (S, nz): lift(x+)
+  double* x_prev;  // ctx-owned (S, n):  x before the plant step (tank C regression)
+};
+
+KMPC_HD inline int loop_nzq(const kmpc_loop_config& c) { return c.nz + (c.du_aug ? 1 : 0); }
+KMPC_HD inline int loop_ny(const kmpc_loop_config& c) {
+  return c.out_mode == KMPC_OUT_IDENTITY ? loop_nzq(c) : (c.out_mode == KMPC_OUT_C ? c.n : 1);
+}
+
+// QP + plant for scenario s at closed-loop step `step`; `base` = this warp's smem slice.
+KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, int64_t s, int64_t step, int64_t log_slot,
+                                     double* base) {
+  const kmpc_loop_config& c = d.c;
+  const int nz = c.nz, n = c.n, N = c.N;
+  const int nzq = loop_nzq(c);
+  const bool identity = c.out_mode == KMPC_OUT_IDENTITY;
+  const int ny = loop_ny(c);
+  QpWs ws = qp_ws_carve(base, nzq, ny, N, identity);
+  const int64_t sm = c.shared_model ? 0 : s;
+  const double* A = d.b.A + sm * nz * nz;
+  const double* B = d.b.B + sm * nz;
+  const double* C = d.b.C + sm * n * nz;
+  const double uprev = d.b.u_prev[s];
+  // QP model: optional velocity-form augmentation  A <- [A B; 0 1], B <- [B; 1], C <- C [I 0]
+  KMPC_LANE_LOOP(e, nzq * nzq) {
+    const int i = e / nzq, j = e - i * nzq;
+    double v;
+    if (i < nz) v = (j < nz) ? A[i * nz + j] : B[i];
+    else v = (j == nz) ? 1.0 : 0.0;
+    ws.A[e] = v;
+  }
+  KMPC_LANE_LOOP(e, nzq) {
+    ws.B[e] = (e < nz) ? B[e] : 1.0;
+    ws.z0[e] = (e < nz) ? d.b.z[s * nz + e] : uprev;
+  }
+  if (!identity) {
+    KMPC_LANE_LOOP(e, ny * nzq) {
+      const int i = e / nzq, j = e - i * nzq;
+      const int row = (c.out_mode == KMPC_OUT_C) ? i : c.out_row;
+      ws.Cy[e] = (j < nz) ? C[row * nz + j] : 0.0;
+    }
+  }
+  KMPC_LANE_LOOP(e, N) {
+    double lo = c.lb, hi = c.ub;
+    if (c.du_aug && e == 0) {  // Tank_System.m:182-188: umin <= U0 + dU_1 <= umax
+      lo = fmax(lo, c.u_lb - uprev);
+      hi = fmin(hi, c.u_ub - uprev);
+    }
+    ws.lb[e] = lo;
+    ws.ub[e] = hi;
+  }
+  KMPC_SYNCWARP();
+  qp_build_warp(ws, nzq, ny, N, identity, c.q, c.rw, d.b.r + s * ny, 0, nullptr);
+  const int st = qp_solve_warp(ws, N, c.max_iter, c.tol);
+  if (KMPC_LANE0) {
+    const double move = ws.x[0];
+    const double u = c.du_aug ? uprev + move : move;
+    const double* pp = (step < c.first_post_step ? d.b.params_pre : d.b.params_post) + s * 5;
+    double p[5];
+    for (int k = 0; k < 5; ++k) p[k] = pp[k];
+    const double x1 = d.b.x[s * 2], x2 = d.b.x[s * 2 + 1];
+    double o1, o2;
+    plant_step_dev(c.plant_kind, c.rk4_variant, c.h, p, x1, x2, u, o1, o2);
+    d.x_prev[s * 2] = x1;
+    d.x_prev[s * 2 + 1] = x2;
+    d.b.x[s * 2] = o1;
+    d.b.x[s * 2 + 1] = o2;
+    d.b.u_prev[s] = u;
+    if (d.b.log_x && log_slot >= 0) {
+      d.b.log_x[(log_slot * c.S + s) * 2] = o1;
+      d.b.log_x[(log_slot * c.S + s) * 2 + 1] = o2;
+    }
+    if (d.b.log_u && log_slot >= 0) d.b.log_u[log_slot * c.S + s] = u;
+    if (d.b.status && st) d.b.status[s] |= st;
+  }
+}
+
+// RLS with the sample (z, u) -> z_next; afterwards z <- z_next.  `first` = this is the restart
+// update (duffing.py:927-930, 943-946): state is initialised to P = p0 I, bar_Q = q0 I, K_A = 0,
+// bar_X = 0 instead of being read.
+KMPC_DEV void loop_rls_scenario(const LoopDev& d, int64_t s, int first, double* base) {
+  const kmpc_loop_config& c = d.c;
+  const int nz = c.nz, n = c.n, nv = nz + 1;
+  RlsWs ws = rls_ws_carve(base, nz, n);
+  const bool upc = c.rls_flags & KMPC_RLS_UPDATE_C;
+  if (first) {
+    KMPC_LANE_LOOP(e, nz * nv) ws.KA[e] = 0.0;
+    KMPC_LANE_LOOP(e, nv * nv) ws.P[e] = (e / nv == e % nv) ? c.p0 : 0.0;
+    KMPC_LANE_LOOP(e, n * nz) ws.barX[e] = 0.0;
+    KMPC_LANE_LOOP(e, nz * nz) ws.barQ[e] = (e / nz == e % nz) ? c.q0 : 0.0;
+  } else {
+    KMPC_LANE_LOOP(e, nz * nv) ws.KA[e] = d.b.KA[s * nz * nv + e];
+    KMPC_LANE_LOOP(e, nv * nv) ws.P[e] = d.b.P[s * nv * nv + e];
+    if (upc) {
+      KMPC_LANE_LOOP(e, n * nz) ws.barX[e] = d.b.barX[s * n * nz + e];
+      KMPC_LANE_LOOP(e, nz * nz) ws.barQ[e] = d.b.barQ[s * nz * nz + e];
+    }
+  }
+  KMPC_LANE_LOOP(e, nz) {
+    ws.v[e] = d.b.z[s * nz + e];
+    ws.y[e] = d.z_next[s * nz + e];
+  }
+  if (KMPC_LANE0) ws.v[nz] = d.b.u_prev[s];
+  KMPC_LANE_LOOP(e, n) ws.xc[e] = c.c_pairs_next ? d.b.x[s * n + e] : d.x_prev[s * n + e];
+  KMPC_SYNCWARP();
+  int flags = c.rls_flags;
+  if (first && c.skip_first_barx) flags |= KMPC_RLS_SKIP_BARX;
+  rls_update_warp(ws, nz, n, c.lambda, flags, d.b.A + s * nz * nz, d.b.B + s * nz, d.b.C + s * n * nz);
+  KMPC_LANE_LOOP(e, nz * nv) d.b.KA[s * nz * nv + e] = ws.KA[e];
+  KMPC_LANE_LOOP(e, nv * nv) d.b.P[s * nv * nv + e] = ws.P[e];
+  if (upc) {
+    KMPC_LANE_LOOP(e, n * nz) d.b.barX[s * n * nz + e] = ws.barX[e];
+    KMPC_LANE_LOOP(e, nz * nz) d.b.barQ[s * nz * nz + e] = ws.barQ[e];
+  }
+  KMPC_LANE_LOOP(e, nz) d.b.z[s * nz + e] = ws.y[e];
+}
+
+}  // namespace kmpc

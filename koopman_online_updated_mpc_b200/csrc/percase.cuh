@@ -1,0 +1,572 @@
+// percase.cuh -- warp-per-scenario device functions: RLS update, condensed-QP build, exact
+// box-QP active-set solve, plant step, small SPD solves.
+//
+// Mapping: ONE WARP owns one scenario; all per-scenario matrices live in that warp's slice of
+// shared memory; work inside a phase is distributed over lanes with a lane-strided loop and
+// phases are separated by __syncwarp().  fp64 throughout (fp32 RLS diverges).
+//
+// The same source compiles with a host compiler when KMPC_HOSTEMU is defined: a lane-strided
+// loop becomes a plain loop over all elements and the warp primitives become no-ops.  That build
+// exists only for tests/hostemu (kernel-logic checks on machines without a GPU); it is never
+// loaded by the product package.
+//
+// Reference semantics: RLS duffing.py:927-953, Koopman_update.m:258-278, Tank_System.m:234-263;
+// QP Tank_System.m:128-159,182-188 == duffing.py:540-581 + 776-778; plant duffing.py:250-261,
+// Koopman_update.m:21-25, Tank_System.m:9-10,211.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/kmpc.h"
+
+#ifdef KMPC_HOSTEMU
+#define KMPC_DEV inline
+#define KMPC_HD
+#define KMPC_LANE_LOOP(e, n) for (int e = 0; e < (n); ++e)
+#define KMPC_SYNCWARP() ((void)0)
+#define KMPC_LANE0 true
+#else
+#define KMPC_DEV __device__ __forceinline__
+#define KMPC_HD __host__ __device__
+#define KMPC_LANE_LOOP(e, n) for (int e = (int)(threadIdx.x & 31); e < (n); e += 32)
+#define KMPC_SYNCWARP() __syncwarp()
+#define KMPC_LANE0 ((threadIdx.x & 31) == 0)
+#endif
+
+namespace kmpc {
+
+// ---------------------------------------------------------------- warp reductions -----------
+// (value, index) argmin with lowest-index tie break; host build: identity.
+KMPC_DEV void warp_argmin(double& val, int& idx) {
+#ifndef KMPC_HOSTEMU
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, val, off);
+    int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+    if (ov < val || (ov == val && oi < idx)) {
+      val = ov;
+      idx = oi;
+    }
+  }
+#endif
+}
+KMPC_DEV double warp_max(double v) {
+#ifndef KMPC_HOSTEMU
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+#endif
+  return v;
+}
+KMPC_DEV int warp_or(int v) {
+#ifndef KMPC_HOSTEMU
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, off);
+#endif
+  return v;
+}
+
+// ---------------------------------------------------------------- plant ---------------------
+KMPC_DEV void poly2_rhs(double x1, double x2, double u, const double* p, double& d1, double& d2) {
+  d1 = p[0] * x2;
+  d2 = p[1] * x2 + p[2] * x1 + p[3] * (x1 * x1 * x1) + p[4] * (x1 * x1 * x2) + u;
+}
+
+// one plant step for one scenario (scalar code; called by one lane or by every lane redundantly)
+KMPC_DEV void plant_step_dev(int kind, int rk4_variant, double h, const double* p, double x1,
+                             double x2, double u, double& o1, double& o2) {
+  if (kind == KMPC_PLANT_POLY2) {
+    double k1a, k1b, k2a, k2b, k3a, k3b, k4a, k4b;
+    poly2_rhs(x1, x2, u, p, k1a, k1b);
+    poly2_rhs(x1 + 0.5 * h * k1a, x2 + 0.5 * h * k1b, u, p, k2a, k2b);
+    poly2_rhs(x1 + 0.5 * h * k2a, x2 + 0.5 * h * k2b, u, p, k3a, k3b);
+    if (rk4_variant == KMPC_RK4_PYTHON)
+      poly2_rhs(x1 + h * k3a, x2 + h * k3b, u, p, k4a, k4b);
+    else  // Koopman_update.m:24: k4 = f(x + k1*dt)
+      poly2_rhs(x1 + h * k1a, x2 + h * k1b, u, p, k4a, k4b);
+    o1 = x1 + (h / 6.0) * (k1a + 2.0 * k2a + 2.0 * k3a + k4a);
+    o2 = x2 + (h / 6.0) * (k1b + 2.0 * k2b + 2.0 * k3b + k4b);
+  } else {  // Tank_System.m:9-10 + clamp l.211
+    double s1 = sqrt(x1), s2 = sqrt(x2);
+    o1 = x1 - p[0] * s1 + p[1] * u;
+    o2 = x2 + p[2] * s1 - p[3] * s2;
+    if (o1 < 0.0) o1 = 0.0;
+    if (o2 < 0.0) o2 = 0.0;
+  }
+}
+
+// ---------------------------------------------------------------- RBF lift -------------------
+KMPC_DEV double rbf_thinplate(const double* x, const double* c, int n, int variant) {
+  double r2 = 0.0;
+  for (int k = 0; k < n; ++k) {
+    double d = x[k] - c[k];
+    r2 += d * d;
+  }
+  if (variant == KMPC_RBF_PYTHON) return r2 * log(sqrt(r2) + 1e-4);  // duffing_RBF.py:22
+  if (r2 == 0.0) return 0.0;                                          // rbf.m:26-28 (NaN -> 0)
+  return r2 * log(sqrt(r2));
+}
+
+// ---------------------------------------------------------------- RLS ------------------------
+// Shared-memory workspace of one scenario (doubles).
+struct RlsWs {
+  double *KA, *P, *barX, *barQ;  // state: nz*nv, nv*nv, n*nz, nz*nz
+  double *v, *y, *xc;            // sample: nv (= [z;u]), nz, n
+  double *w, *rrow;              // P v, v'P (nv each; reused for bar_Q with nz)
+};
+KMPC_HD inline int rls_ws_doubles(int nz, int n) {
+  int nv = nz + 1;
+  return nz * nv + nv * nv + n * nz + nz * nz + nv + nz + n + 2 * nv;
+}
+KMPC_DEV RlsWs rls_ws_carve(double* base, int nz, int n) {
+  int nv = nz + 1;
+  RlsWs w;
+  w.KA = base;
+  w.P = w.KA + nz * nv;
+  w.barX = w.P + nv * nv;
+  w.barQ = w.barX + n * nz;
+  w.v = w.barQ + nz * nz;
+  w.y = w.v + nv;
+  w.xc = w.y + nz;
+  w.w = w.xc + n;
+  w.rrow = w.w + nv;
+  return w;
+}
+
+// State and sample already in ws.  Writes A (nz*nz), B (nz), C (n*nz) through the given pointers
+// (global or shared).  Formula order follows the reference (no symmetrisation of P).
+KMPC_DEV void rls_update_warp(const RlsWs& ws, int nz, int n, double lam, int flags, double* oA,
+                              double* oB, double* oC) {
+  const int nv = nz + 1;
+  // w = P v (lanes 0..nv-1), rrow = v'P (next nv)
+  KMPC_LANE_LOOP(o, 2 * nv) {
+    double s = 0.0;
+    if (o < nv) {
+      for (int j = 0; j < nv; ++j) s += ws.P[o * nv + j] * ws.v[j];
+      ws.w[o] = s;
+    } else {
+      int j = o - nv;
+      for (int i = 0; i < nv; ++i) s += ws.v[i] * ws.P[i * nv + j];
+      ws.rrow[j] = s;
+    }
+  }
+  KMPC_SYNCWARP();
+  double vPv = 0.0;  // (v'P) v, duffing.py:934
+  for (int j = 0; j < nv; ++j) vPv += ws.rrow[j] * ws.v[j];
+  const double denom = lam + vPv;
+  KMPC_LANE_LOOP(e, nv * nv) {
+    int i = e / nv, j = e - i * nv;
+    ws.P[e] = ws.P[e] / lam - (ws.w[i] * ws.rrow[j]) / lam / denom;
+  }
+  KMPC_LANE_LOOP(e, nz * nv) {
+    int i = e / nv, j = e - i * nv;
+    ws.KA[e] += ws.y[i] * ws.v[j];
+  }
+  KMPC_SYNCWARP();
+  KMPC_LANE_LOOP(e, nz * nv) {  // [A B] = K_A P
+    int i = e / nv, j = e - i * nv;
+    double s = 0.0;
+    for (int k = 0; k < nv; ++k) s += ws.KA[i * nv + k] * ws.P[k * nv + j];
+    if (j < nz)
+      oA[i * nz + j] = s;
+    else
+      oB[i] = s;
+  }
+  if (flags & KMPC_RLS_UPDATE_C) {
+    KMPC_SYNCWARP();
+    KMPC_LANE_LOOP(o, 2 * nz) {  // w = bar_Q z, rrow = z' bar_Q  (z = v[0..nz))
+      double s = 0.0;
+      if (o < nz) {
+        for (int j = 0; j < nz; ++j) s += ws.barQ[o * nz + j] * ws.v[j];
+        ws.w[o] = s;
+      } else {
+        int j = o - nz;
+        for (int i = 0; i < nz; ++i) s += ws.v[i] * ws.barQ[i * nz + j];
+        ws.rrow[j] = s;
+      }
+    }
+    KMPC_SYNCWARP();
+    double zQz = 0.0;
+    for (int j = 0; j < nz; ++j) zQz += ws.rrow[j] * ws.v[j];
+    const double dq = 1.0 + zQz;
+    KMPC_LANE_LOOP(e, nz * nz) {
+      int i = e / nz, j = e - i * nz;
+      ws.barQ[e] = ws.barQ[e] - (ws.w[i] * ws.rrow[j]) / dq;
+    }
+    if (!(flags & KMPC_RLS_SKIP_BARX)) {
+      KMPC_LANE_LOOP(e, n * nz) {
+        int i = e / nz, j = e - i * nz;
+        ws.barX[e] += ws.xc[i] * ws.v[j];
+      }
+    }
+    KMPC_SYNCWARP();
+    KMPC_LANE_LOOP(e, n * nz) {  // C = bar_X bar_Q
+      int i = e / nz, j = e - i * nz;
+      double s = 0.0;
+      for (int k = 0; k < nz; ++k) s += ws.barX[i * nz + k] * ws.barQ[k * nz + j];
+      oC[e] = s;
+    }
+  }
+  KMPC_SYNCWARP();
+}
+
+// ---------------------------------------------------------------- QP -------------------------
+// Packed lower-triangular index.
+KMPC_HD inline int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+struct QpWs {
+  double *A, *B, *Cy;   // model: nzq*nzq, nzq, ny*nzq (Cy unused when identity)
+  double *z0;           // nzq
+  double *VB, *VZ;      // N*nzq each: VB[t] = A^t B, VZ[t] = A^(t+1) z0
+  double *g, *e;        // N*ny each (alias VB / VZ when Cy = I)
+  double *H, *L;        // packed lower N(N+1)/2 each: H, Cholesky factor of the free block of 2H
+  double *invd;         // N
+  double *f, *x, *p, *grad, *lb, *ub;  // N each
+  int* W;               // N working-set flags: -1 at lower, +1 at upper, 0 free
+};
+KMPC_HD inline int qp_ws_doubles(int nzq, int ny, int N, bool identity) {
+  int t = nzq * nzq + nzq + (identity ? 0 : ny * nzq) + nzq + 2 * N * nzq +
+          (identity ? 0 : 2 * N * ny) + N * (N + 1) + 7 * N + (N + 1) / 2;
+  return (t + 1) & ~1;  // keep every warp slice 16-byte aligned
+}
+KMPC_DEV QpWs qp_ws_carve(double* base, int nzq, int ny, int N, bool identity) {
+  QpWs w;
+  double* p = base;
+  w.A = p; p += nzq * nzq;
+  w.B = p; p += nzq;
+  w.Cy = p; p += identity ? 0 : ny * nzq;
+  w.z0 = p; p += nzq;
+  w.VB = p; p += N * nzq;
+  w.VZ = p; p += N * nzq;
+  if (identity) {
+    w.g = w.VB;
+    w.e = w.VZ;
+  } else {
+    w.g = p; p += N * ny;
+    w.e = p; p += N * ny;
+  }
+  w.H = p; p += N * (N + 1) / 2;
+  w.L = p; p += N * (N + 1) / 2;
+  w.invd = p; p += N;
+  w.f = p; p += N;
+  w.x = p; p += N;
+  w.p = p; p += N;
+  w.grad = p; p += N;
+  w.lb = p; p += N;
+  w.ub = p; p += N;
+  w.W = reinterpret_cast<int*>(p);
+  return w;
+}
+
+// Build H (packed) and f from the model in ws (A, B, Cy, z0) and the reference r.
+//   r_stride = 0: r is (ny) constant over the horizon; r_stride = ny: r is (N, ny).
+//   PN: optional terminal weight (ny*ny, row-major) replacing the last q*I block (nullable).
+KMPC_DEV void qp_build_warp(const QpWs& ws, int nzq, int ny, int N, bool identity, double q,
+                            double rw, const double* r, int r_stride, const double* PN) {
+  // ---- Krylov chains: VZ[t] = A VZ[t-1] (VZ[-1] = z0), VB[t+1] = A VB[t] (VB[0] = B);
+  //      lanes 0-15 advance the z chain, lanes 16-31 the B chain (nzq <= 16)
+  KMPC_LANE_LOOP(i, nzq) ws.VB[i] = ws.B[i];
+  KMPC_SYNCWARP();
+  for (int t = 0; t < N; ++t) {
+    KMPC_LANE_LOOP(o, 32) {
+      const int half = o >> 4, i = o & 15;
+      if (i < nzq) {
+        if (half == 0) {
+          const double* src = (t == 0) ? ws.z0 : ws.VZ + (t - 1) * nzq;
+          double s = 0.0;
+          for (int j = 0; j < nzq; ++j) s += ws.A[i * nzq + j] * src[j];
+          ws.VZ[t * nzq + i] = s;
+        } else if (t + 1 < N) {
+          const double* src = ws.VB + t * nzq;
+          double s = 0.0;
+          for (int j = 0; j < nzq; ++j) s += ws.A[i * nzq + j] * src[j];
+          ws.VB[(t + 1) * nzq + i] = s;
+        }
+      }
+    }
+    KMPC_SYNCWARP();
+  }
+  // ---- outputs: g[t] = Cy VB[t], e[t] = Cy VZ[t] - r[t]
+  if (identity) {
+    KMPC_LANE_LOOP(o, N * ny) {
+      int t = o / ny, c = o - t * ny;
+      ws.e[o] = ws.VZ[o] - r[t * r_stride + c];
+    }
+  } else {
+    KMPC_LANE_LOOP(o, 2 * N * ny) {
+      int which = o / (N * ny), oo = o - which * N * ny;
+      int t = oo / ny, c = oo - t * ny;
+      const double* src = (which == 0 ? ws.VB : ws.VZ) + t * nzq;
+      double s = 0.0;
+      for (int j = 0; j < nzq; ++j) s += ws.Cy[c * nzq + j] * src[j];
+      if (which == 0)
+        ws.g[oo] = s;
+      else
+        ws.e[oo] = s - r[t * r_stride + c];
+    }
+  }
+  KMPC_SYNCWARP();
+  // ---- H along diagonals: H[a][a-d] = q * sum_{t=0}^{N-1-a} <g[t+d], g[t]>  (+ rw on d = 0)
+  KMPC_LANE_LOOP(d, N) {
+    double run = 0.0;
+    for (int t = 0; t + d < N; ++t) {
+      double s = 0.0;
+      for (int c = 0; c < ny; ++c) s += ws.g[(t + d) * ny + c] * ws.g[t * ny + c];
+      run += q * s;
+      int a = N - 1 - t;
+      ws.H[tri(a, a - d)] = run + (d == 0 ? rw : 0.0);
+    }
+  }
+  // ---- f[a] = 2 q sum_{k=a}^{N-1} <g[k-a], e[k]>
+  KMPC_LANE_LOOP(a, N) {
+    double s = 0.0;
+    for (int k = a; k < N; ++k)
+      for (int c = 0; c < ny; ++c) s += ws.g[(k - a) * ny + c] * ws.e[k * ny + c];
+    ws.f[a] = 2.0 * q * s;
+  }
+  KMPC_SYNCWARP();
+  if (PN != nullptr) {
+    // terminal block: H[a][b] += g[N-1-a]' (PN - qI) g[N-1-b],  f[a] += 2 g[N-1-a]' (PN - qI) e[N-1]
+    KMPC_LANE_LOOP(a, N) {
+      double s = 0.0;
+      for (int c = 0; c < ny; ++c)
+        for (int k = 0; k < ny; ++k)
+          s += ws.g[(N - 1 - a) * ny + c] * (PN[c * ny + k] - (c == k ? q : 0.0)) *
+               ws.e[(N - 1) * ny + k];
+      ws.f[a] += 2.0 * s;
+    }
+    KMPC_LANE_LOOP(pr, N * (N + 1) / 2) {
+      int a = (int)((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
+      while (tri(a + 1, 0) <= pr) ++a;
+      while (tri(a, 0) > pr) --a;
+      const int b = pr - tri(a, 0);
+      double s = 0.0;
+      for (int c = 0; c < ny; ++c)
+        for (int k = 0; k < ny; ++k)
+          s += ws.g[(N - 1 - a) * ny + c] * (PN[c * ny + k] - (c == k ? q : 0.0)) *
+               ws.g[(N - 1 - b) * ny + k];
+      ws.H[pr] += s;
+    }
+    KMPC_SYNCWARP();
+  }
+}
+
+// Cholesky of the free block of 2H into ws.L (masked rows/cols become identity rows).
+// Returns KMPC_STATUS_PIVOT if a pivot was not positive.
+KMPC_DEV int qp_chol_masked(const QpWs& ws, int N) {
+  int status = 0;
+  for (int j = 0; j < N; ++j) {
+    const bool mj = ws.W[j] != 0;  // warp-uniform
+    KMPC_LANE_LOOP(ii, N - j) {
+      int i = j + ii;
+      double s = 0.0;
+      if (!mj && ws.W[i] == 0) {
+        s = 2.0 * ws.H[tri(i, j)];
+        for (int k = 0; k < j; ++k) s -= ws.L[tri(i, k)] * ws.L[tri(j, k)];
+      }
+      ws.L[tri(i, j)] = s;  // unscaled column
+    }
+    KMPC_SYNCWARP();
+    double d = mj ? 1.0 : ws.L[tri(j, j)];
+    if (!(d > 0.0)) {
+      status |= KMPC_STATUS_PIVOT;
+      d = 1e-300;
+    }
+    const double piv = sqrt(d);
+    const double inv = 1.0 / piv;
+    KMPC_SYNCWARP();  // everyone has read L[j][j] before it is overwritten
+    KMPC_LANE_LOOP(ii, N - j) {
+      int i = j + ii;
+      if (ii == 0) {
+        ws.L[tri(j, j)] = piv;
+        ws.invd[j] = inv;
+      } else {
+        ws.L[tri(i, j)] *= inv;
+      }
+    }
+    KMPC_SYNCWARP();
+  }
+  return status;
+}
+
+// Solve (L L') p = rhs in place in ws.p (rhs must be zero on masked entries).
+KMPC_DEV void qp_chol_solve(const QpWs& ws, int N) {
+  for (int j = 0; j < N; ++j) {  // forward, column oriented
+    const double yj = ws.p[j] * ws.invd[j];
+    KMPC_SYNCWARP();
+    KMPC_LANE_LOOP(ii, N - j) {
+      int i = j + ii;
+      if (ii == 0)
+        ws.p[j] = yj;
+      else
+        ws.p[i] -= ws.L[tri(i, j)] * yj;
+    }
+    KMPC_SYNCWARP();
+  }
+  for (int j = N - 1; j >= 0; --j) {  // backward
+    const double xj = ws.p[j] * ws.invd[j];
+    KMPC_SYNCWARP();
+    KMPC_LANE_LOOP(i, j + 1) {
+      if (i == j)
+        ws.p[j] = xj;
+      else
+        ws.p[i] -= ws.L[tri(j, i)] * xj;
+    }
+    KMPC_SYNCWARP();
+  }
+}
+
+// grad = 2 H x + f
+KMPC_DEV void qp_gradient(const QpWs& ws, int N) {
+  KMPC_LANE_LOOP(i, N) {
+    double s = 0.0;
+    for (int j = 0; j < N; ++j) s += ws.H[i >= j ? tri(i, j) : tri(j, i)] * ws.x[j];
+    ws.grad[i] = 2.0 * s + ws.f[i];
+  }
+  KMPC_SYNCWARP();
+}
+
+// Exact primal active-set solve of  min x'Hx + f'x,  lb <= x <= ub  (oracle/mpc.py
+// solve_box_qp_exact is the same algorithm).  Result in ws.x; returns status bits.
+KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol) {
+  int status = 0;
+  KMPC_LANE_LOOP(i, N) {
+    ws.W[i] = 0;
+    ws.p[i] = -ws.f[i];
+  }
+  KMPC_SYNCWARP();
+  status |= qp_chol_masked(ws, N);
+  qp_chol_solve(ws, N);
+  int any = 0;
+  double fmaxabs = 0.0;
+  KMPC_LANE_LOOP(i, N) {
+    double xi = ws.p[i];
+    int w = 0;
+    if (xi < ws.lb[i]) {
+      w = -1;
+      xi = ws.lb[i];
+    } else if (xi > ws.ub[i]) {
+      w = 1;
+      xi = ws.ub[i];
+    }
+    ws.W[i] = w;
+    ws.x[i] = xi;
+    any |= (w != 0);
+    fmaxabs = fmax(fmaxabs, fabs(ws.f[i]));
+  }
+  any = warp_or(any);
+  fmaxabs = warp_max(fmaxabs);
+  KMPC_SYNCWARP();
+  if (any) {
+    const double mtol = tol * fmax(1.0, fmaxabs);
+    bool done = false;
+    for (int it = 0; it < max_iter && !done; ++it) {
+      qp_gradient(ws, N);
+      KMPC_LANE_LOOP(i, N) ws.p[i] = (ws.W[i] == 0) ? -ws.grad[i] : 0.0;
+      KMPC_SYNCWARP();
+      status |= qp_chol_masked(ws, N);
+      qp_chol_solve(ws, N);
+      // ratio test
+      double alpha = 1.0;
+      int block = 0x7fffffff;
+      KMPC_LANE_LOOP(i, N) {
+        if (ws.W[i] == 0) {
+          double pi = ws.p[i], xi = ws.x[i], a = 2.0;
+          if (pi > 0.0 && xi + pi > ws.ub[i])
+            a = (ws.ub[i] - xi) / pi;
+          else if (pi < 0.0 && xi + pi < ws.lb[i])
+            a = (ws.lb[i] - xi) / pi;
+          if (a < alpha) {  // strict: lowest index wins ties within a lane's ascending sweep
+            alpha = a;
+            block = i;
+          }
+        }
+      }
+      warp_argmin(alpha, block);
+      const bool blocked = block != 0x7fffffff;
+      KMPC_LANE_LOOP(i, N) {
+        double xi = ws.x[i] + alpha * ws.p[i];
+        if (blocked && i == block) {
+          const int side = ws.p[i] > 0.0 ? 1 : -1;
+          xi = side > 0 ? ws.ub[i] : ws.lb[i];
+          ws.W[i] = side;
+        }
+        ws.x[i] = xi;
+      }
+      KMPC_SYNCWARP();
+      if (blocked) continue;
+      // full step taken: multipliers of the bound variables
+      qp_gradient(ws, N);
+      double worst = INFINITY;
+      int widx = 0x7fffffff;
+      KMPC_LANE_LOOP(i, N) {
+        const int w = ws.W[i];
+        if (w != 0) {
+          const double lam = w < 0 ? ws.grad[i] : -ws.grad[i];
+          if (lam < worst) {
+            worst = lam;
+            widx = i;
+          }
+        }
+      }
+      warp_argmin(worst, widx);
+      if (widx == 0x7fffffff || worst >= -mtol) {
+        done = true;
+      } else {
+        if (KMPC_LANE0) ws.W[widx] = 0;
+        KMPC_SYNCWARP();
+      }
+    }
+    if (!done) status |= KMPC_STATUS_MAXITER;
+  }
+  int bad = 0;
+  KMPC_LANE_LOOP(i, N) bad |= !isfinite(ws.x[i]);
+  if (warp_or(bad)) status |= KMPC_STATUS_NONFINITE;
+  return status;
+}
+
+// ---------------------------------------------------------------- small SPD solve ------------
+// X = Bm * inv(G) for SPD G (n x n, row-major, destroyed) and Bm (rows x n): Cholesky of G then
+// two triangular solves per row.  Used by the EDMD solve (K = Aq G^-1).  Work arrays in smem or
+// global; single warp.
+KMPC_DEV int spd_right_solve_warp(double* G, int n, double* Bm, int rows) {
+  int status = 0;
+  for (int j = 0; j < n; ++j) {  // in-place lower Cholesky, left-looking
+    KMPC_LANE_LOOP(ii, n - j) {
+      int i = j + ii;
+      double s = G[i * n + j];
+      for (int k = 0; k < j; ++k) s -= G[i * n + k] * G[j * n + k];
+      G[i * n + j] = s;
+    }
+    KMPC_SYNCWARP();
+    double d = G[j * n + j];
+    if (!(d > 0.0)) {
+      status |= KMPC_STATUS_PIVOT;
+      d = 1e-300;
+    }
+    const double piv = sqrt(d);
+    KMPC_SYNCWARP();
+    KMPC_LANE_LOOP(ii, n - j) {
+      int i = j + ii;
+      G[i * n + j] = (ii == 0) ? piv : G[i * n + j] / piv;
+    }
+    KMPC_SYNCWARP();
+  }
+  // each row b of Bm solves  x (L L') = b  ->  L L' x' = b'
+  KMPC_LANE_LOOP(rr, rows) {
+    double* b = Bm + rr * n;
+    for (int i = 0; i < n; ++i) {
+      double s = b[i];
+      for (int k = 0; k < i; ++k) s -= G[i * n + k] * b[k];
+      b[i] = s / G[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      double s = b[i];
+      for (int k = i + 1; k < n; ++k) s -= G[k * n + i] * b[k];
+      b[i] = s / G[i * n + i];
+    }
+  }
+  KMPC_SYNCWARP();
+  return status;
+}
+
+}  // namespace kmpc
