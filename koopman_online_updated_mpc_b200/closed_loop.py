@@ -85,6 +85,19 @@ def tank_spec(nz=10, **kw):
                             params_pre=_plant.TANK_PRE, params_post=_plant.TANK_POST), **kw)
 
 
+def make_config(spec, S, shared_model, log_steps=0):
+    """LoopSpec -> the C struct kmpc_loop_config (include/kmpc.h)."""
+    return _lib.LoopConfigC(
+        S=S, nz=spec.nz, n=spec.n, N=spec.N, out_mode=spec.out_mode, out_row=spec.out_row,
+        du_aug=int(spec.du_aug), update=int(spec.update), rls_flags=(1 if spec.update_c else 0),
+        c_pairs_next=int(spec.c_pairs_next), skip_first_barx=int(spec.skip_first_barx),
+        shared_model=int(shared_model), lift_kind=spec.lift_kind, lift_mode=spec.lift_mode,
+        plant_kind=spec.plant_kind, rk4_variant=spec.rk4_variant,
+        first_post_step=spec.first_post_step, max_iter=spec.max_iter, h=spec.h, q=spec.q,
+        rw=spec.rw, lb=spec.lb, ub=spec.ub, u_lb=spec.u_lb, u_ub=spec.u_ub, lam=spec.lam,
+        p0=spec.p0, q0=spec.q0, tol=spec.tol)
+
+
 class ClosedLoop:
     """Device-resident batch of S closed-loop scenarios.
 
@@ -143,15 +156,7 @@ class ClosedLoop:
         self.log_x = torch.zeros((log_steps, S, n), **f64) if log_steps else None
         self.log_u = torch.zeros((log_steps, S), **f64) if log_steps else None
         self.status = torch.zeros(S, dtype=torch.int32, device="cuda")
-        cfg = _lib.LoopConfigC(
-            S=S, nz=nz, n=n, N=spec.N, out_mode=spec.out_mode, out_row=spec.out_row,
-            du_aug=int(spec.du_aug), update=int(spec.update), rls_flags=(1 if spec.update_c else 0),
-            c_pairs_next=int(spec.c_pairs_next), skip_first_barx=int(spec.skip_first_barx),
-            shared_model=int(shared), lift_kind=spec.lift_kind, lift_mode=spec.lift_mode,
-            plant_kind=spec.plant_kind, rk4_variant=spec.rk4_variant,
-            first_post_step=spec.first_post_step, max_iter=spec.max_iter, h=spec.h, q=spec.q,
-            rw=spec.rw, lb=spec.lb, ub=spec.ub, u_lb=spec.u_lb, u_ub=spec.u_ub, lam=spec.lam,
-            p0=spec.p0, q0=spec.q0, tol=spec.tol)
+        cfg = make_config(spec, S, shared, log_steps)
         rs = self.rls
         buf = _lib.LoopBuffersC(
             x=ptr(self.x), z=ptr(self.z), u_prev=ptr(self.u_prev), A=ptr(self.A), B=ptr(self.B),

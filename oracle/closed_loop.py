@@ -128,7 +128,7 @@ def mpc_move(cfg, A, B, C, zl, u_prev, qp="exact"):
 
 
 def run_loop(cfg, A, B, C, x0, T, update=UPDATE_RLS, qp="exact", warm=None, storage=None,
-             u_prev=0.0, record_models=False, start_step=0):
+             u_prev=0.0, record_models=False, start_step=0, record_states=False):
     """Run T closed-loop steps for one scenario.  `warm` = rls.RLSState to continue from
     (Koopman_update.m:264-265); `storage` = dict(PHIX, PHIY, U, X) for the literal storage-method
     update of duffing_RBF.py:406-438.  Returns a dict of logs and the final model/state."""
@@ -136,12 +136,15 @@ def run_loop(cfg, A, B, C, x0, T, update=UPDATE_RLS, qp="exact", warm=None, stor
     A, B, C = (np.array(M, dtype=np.float64) for M in (A, B, C))
     B = B.reshape(-1, 1)
     st = warm
-    logX, logU, logZ, logStatus, models = [], [], [], [], []
+    logX, logU, logZ, logStatus, models, pre_states = [], [], [], [], [], []
     if update == UPDATE_STORAGE:
         X_EX, Y_EX = storage["PHIX"].copy(), storage["PHIY"].copy()
         U_EX, Xs = storage["U"].copy(), storage["X"].copy()
     zl = cfg.lift_fn(x)
     for k in range(start_step, start_step + T):
+        if record_states:  # everything step k starts from (teacher-forcing fixtures)
+            pre_states.append(dict(k=k, x=x.copy(), z=zl.copy(), u_prev=u_prev, A=A.copy(), B=B.copy(),
+                                   C=C.copy(), rls=None if st is None else st.copy()))
         u, _, status = mpc_move(cfg, A, B, C, zl, u_prev, qp)
         p = cfg.p_pre if k < cfg.first_post_step else cfg.p_post
         xn = plant.plant_step(cfg.plant_kind, x, u, np.asarray(p), cfg.h, cfg.rk4_variant)
@@ -175,4 +178,4 @@ def run_loop(cfg, A, B, C, x0, T, update=UPDATE_RLS, qp="exact", warm=None, stor
             models.append((A.copy(), B.copy(), C.copy()))
         x, zl, u_prev = xn, yl, u
     return dict(X=np.array(logX), U=np.array(logU), Z=np.array(logZ), status=np.array(logStatus),
-                A=A, B=B, C=C, rls=st, x=x, u_prev=u_prev, models=models)
+                A=A, B=B, C=C, rls=st, x=x, u_prev=u_prev, models=models, pre_states=pre_states)

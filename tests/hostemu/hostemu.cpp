@@ -9,7 +9,7 @@
 
 #include <vector>
 
-#include "../../koopman_online_updated_mpc_b200/csrc/percase.cuh"
+#include "../../koopman_online_updated_mpc_b200/csrc/loopbody.cuh"
 
 using namespace kmpc;
 
@@ -95,6 +95,77 @@ int emu_rbf_lift(const double* x, const double* cx, double* z, int64_t S, int n,
 // X = Bm inv(G); G (n x n) is destroyed
 int emu_spd_right_solve(double* G, int n, double* Bm, int rows) {
   return spd_right_solve_warp(G, n, Bm, rows);
+}
+
+// ---- fused closed loop, same schedule as kmpc_closed_loop_steps (closed_loop.cu): per step
+// qp_plant -> lift -> rls.  The MLP lift is a plain host loop here (the CUDA encoder kernel is a
+// block-cooperative GEMM that has no lane-emulation; it is checked on the GPU).
+static void host_mlp(int n_layers, const int* dims, const double* const* W, const double* const* b,
+                     const double* x, double* out) {
+  std::vector<double> h(x, x + dims[0]), t;
+  for (int l = 0; l < n_layers; ++l) {
+    t.assign(dims[l + 1], 0.0);
+    for (int o = 0; o < dims[l + 1]; ++o) {
+      double s = b[l][o];
+      for (int k = 0; k < dims[l]; ++k) s += W[l][(size_t)o * dims[l] + k] * h[k];
+      t[o] = (l + 1 < n_layers && s < 0.0) ? 0.0 : s;
+    }
+    h.swap(t);
+  }
+  for (size_t i = 0; i < h.size(); ++i) out[i] = h[i];
+}
+
+static void host_lift(const kmpc_loop_config& c, const kmpc_loop_buffers& b, int n_layers,
+                      const int* dims, const double* const* W, const double* const* bias,
+                      const double* x, double* z) {
+  if (c.lift_kind == KMPC_LIFTKIND_RBF) {
+    for (int k = 0; k < c.nz; ++k) z[k] = rbf_thinplate(x, b.cx + k * c.n, c.n, c.lift_mode);
+    return;
+  }
+  const int nzo = dims[n_layers];
+  std::vector<double> t(nzo), t0(nzo), zero(dims[0], 0.0);
+  host_mlp(n_layers, dims, W, bias, x, t.data());
+  if (c.lift_mode == KMPC_LIFT_RAW) {
+    for (int k = 0; k < nzo; ++k) z[k] = t[k];
+    return;
+  }
+  host_mlp(n_layers, dims, W, bias, zero.data(), t0.data());
+  int off = 0;
+  if (c.lift_mode == KMPC_LIFT_STACK) {
+    for (int k = 0; k < dims[0]; ++k) z[k] = x[k];
+    off = dims[0];
+  }
+  for (int k = 0; k < nzo; ++k) z[off + k] = t[k] - t0[k];
+}
+
+int emu_closed_loop(const kmpc_loop_config* cfg, const kmpc_loop_buffers* buf, int T,
+                    int rls_started, int64_t start_step, int n_layers, const int* dims,
+                    const double* const* W, const double* const* bias) {
+  LoopDev d;
+  d.c = *cfg;
+  d.b = *buf;
+  if (d.c.max_iter <= 0) d.c.max_iter = 10 * d.c.N + 20;
+  if (!(d.c.tol > 0.0)) d.c.tol = 1e-10;
+  const kmpc_loop_config& c = d.c;
+  std::vector<double> znext((size_t)c.S * c.nz), xprev((size_t)c.S * c.n);
+  d.z_next = znext.data();
+  d.x_prev = xprev.data();
+  const bool identity = c.out_mode == KMPC_OUT_IDENTITY;
+  std::vector<double> qws(qp_ws_doubles(loop_nzq(c), loop_ny(c), c.N, identity) + 8);
+  std::vector<double> rws(rls_ws_doubles(c.nz, c.n) + 8);
+  int64_t step = start_step;
+  for (int t = 0; t < T; ++t, ++step) {
+    const int64_t slot = step < d.b.log_capacity ? step : -1;
+    for (int64_t s = 0; s < c.S; ++s) loop_qp_plant_scenario(d, s, step, slot, qws.data());
+    double* zdst = c.update ? d.z_next : d.b.z;
+    for (int64_t s = 0; s < c.S; ++s)
+      host_lift(c, d.b, n_layers, dims, W, bias, d.b.x + s * c.n, zdst + s * c.nz);
+    if (c.update) {
+      for (int64_t s = 0; s < c.S; ++s) loop_rls_scenario(d, s, rls_started ? 0 : 1, rws.data());
+      rls_started = 1;
+    }
+  }
+  return 0;
 }
 
 }  // extern "C"
