@@ -202,6 +202,10 @@ int kmpc_ctx_destroy(kmpc_ctx* ctx);
 /* run T scenario-steps for all S scenarios; continues from the ctx's step index */
 int kmpc_closed_loop_steps(kmpc_ctx* ctx, int T, void* stream);
 int64_t kmpc_ctx_step_index(const kmpc_ctx* ctx);
+/* same as kmpc_closed_loop_steps (T <= 1024) but brackets every kernel with CUDA events on
+ * `stream` and returns, after synchronising, the summed device time in milliseconds of
+ * ms[0] = QP+plant kernels, ms[1] = lift kernels, ms[2] = RLS kernels (bench.py's roofline) */
+int kmpc_closed_loop_steps_timed(kmpc_ctx* ctx, int T, void* stream, float* ms);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,7 @@ _PROTOS = {
     "kmpc_ctx_destroy": (_i, [_vp]),
     "kmpc_closed_loop_steps": (_i, [_vp, _i, _vp]),
     "kmpc_ctx_step_index": (_i64, [_vp]),
+    "kmpc_closed_loop_steps_timed": (_i, [_vp, _i, _vp, _c.POINTER(_c.c_float)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

@@ -180,6 +180,13 @@ class ClosedLoop:
         _lib.check(_lib.lib().kmpc_closed_loop_steps(self._h, int(T), stream_ptr()))
         return self
 
+    def run_timed(self, T):
+        """run(T) with per-kernel CUDA-event timing; returns summed device milliseconds
+        {"qp_plant": .., "lift": .., "rls": ..} (synchronises)."""
+        ms = (ctypes.c_float * 3)()
+        _lib.check(_lib.lib().kmpc_closed_loop_steps_timed(self._h, int(T), stream_ptr(), ms))
+        return {"qp_plant": ms[0], "lift": ms[1], "rls": ms[2]}
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().kmpc_ctx_destroy(self._h)

@@ -6,6 +6,7 @@
 // state resident in caller-owned device buffers (so a step's HBM traffic is exactly the
 // algorithmic bytes of SURVEY.md 8d: RLS state read+write, A/B/C write, x/u/z).
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 #include "loopbody.cuh"
@@ -109,31 +110,63 @@ int kmpc_ctx_destroy(kmpc_ctx* ctx) {
 
 int64_t kmpc_ctx_step_index(const kmpc_ctx* ctx) { return ctx ? ctx->step : -1; }
 
-int kmpc_closed_loop_steps(kmpc_ctx* ctx, int T, void* stream) {
-  if (!ctx || T < 0) return KMPC_ERR_ARG;
+// One closed-loop step = qp_plant kernel -> lift kernel -> (rls kernel).  `ev` (nullable) points at
+// 4 events recorded around the three launches (kmpc_closed_loop_steps_timed).
+static int run_one_step(kmpc_ctx* ctx, void* stream, cudaEvent_t* ev) {
   cudaStream_t st = as_stream(stream);
   const kmpc_loop_config& c = ctx->d.c;
   const unsigned grid = (unsigned)((c.S + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  for (int t = 0; t < T; ++t) {
-    const int64_t slot = (ctx->step < ctx->d.b.log_capacity) ? ctx->step : -1;
-    loop_qp_plant_kernel<<<grid, kWarpsPerBlock * 32, ctx->qp_smem, st>>>(ctx->d, ctx->step, slot);
+  const int64_t slot = (ctx->step < ctx->d.b.log_capacity) ? ctx->step : -1;
+  if (ev) KMPC_CUDA(cudaEventRecord(ev[0], st));
+  loop_qp_plant_kernel<<<grid, kWarpsPerBlock * 32, ctx->qp_smem, st>>>(ctx->d, ctx->step, slot);
+  KMPC_AFTER_LAUNCH();
+  if (ev) KMPC_CUDA(cudaEventRecord(ev[1], st));
+  // lift(x+): into z_next when the RLS still needs the old z, else straight into z
+  double* zdst = c.update ? ctx->d.z_next : ctx->d.b.z;
+  int rc;
+  if (c.lift_kind == KMPC_LIFTKIND_MLP)
+    rc = kmpc_encode(ctx->enc, ctx->d.b.x, zdst, c.S, c.lift_mode, stream);
+  else
+    rc = kmpc_rbf_lift(ctx->d.b.x, ctx->d.b.cx, zdst, c.S, c.n, c.nz, c.lift_mode, stream);
+  if (rc != KMPC_OK) return rc;
+  if (ev) KMPC_CUDA(cudaEventRecord(ev[2], st));
+  if (c.update) {
+    loop_rls_kernel<<<grid, kWarpsPerBlock * 32, ctx->rls_smem, st>>>(ctx->d, ctx->rls_started ? 0 : 1);
     KMPC_AFTER_LAUNCH();
-    // lift(x+): into z_next when the RLS still needs the old z, else straight into z
-    double* zdst = c.update ? ctx->d.z_next : ctx->d.b.z;
-    int rc;
-    if (c.lift_kind == KMPC_LIFTKIND_MLP)
-      rc = kmpc_encode(ctx->enc, ctx->d.b.x, zdst, c.S, c.lift_mode, stream);
-    else
-      rc = kmpc_rbf_lift(ctx->d.b.x, ctx->d.b.cx, zdst, c.S, c.n, c.nz, c.lift_mode, stream);
+    ctx->rls_started = 1;
+  }
+  if (ev) KMPC_CUDA(cudaEventRecord(ev[3], st));
+  ctx->step += 1;
+  return KMPC_OK;
+}
+
+int kmpc_closed_loop_steps(kmpc_ctx* ctx, int T, void* stream) {
+  if (!ctx || T < 0) return KMPC_ERR_ARG;
+  for (int t = 0; t < T; ++t) {
+    const int rc = run_one_step(ctx, stream, nullptr);
     if (rc != KMPC_OK) return rc;
-    if (c.update) {
-      loop_rls_kernel<<<grid, kWarpsPerBlock * 32, ctx->rls_smem, st>>>(ctx->d, ctx->rls_started ? 0 : 1);
-      KMPC_AFTER_LAUNCH();
-      ctx->rls_started = 1;
-    }
-    ctx->step += 1;
   }
   return KMPC_OK;
+}
+
+int kmpc_closed_loop_steps_timed(kmpc_ctx* ctx, int T, void* stream, float* ms) {
+  if (!ctx || T < 1 || T > 1024 || !ms) return KMPC_ERR_ARG;
+  std::vector<cudaEvent_t> ev((size_t)4 * T);
+  for (auto& e : ev) KMPC_CUDA(cudaEventCreate(&e));
+  int rc = KMPC_OK;
+  for (int t = 0; t < T && rc == KMPC_OK; ++t) rc = run_one_step(ctx, stream, ev.data() + 4 * t);
+  if (rc == KMPC_OK && cudaStreamSynchronize(as_stream(stream)) != cudaSuccess) rc = KMPC_ERR_CUDA;
+  ms[0] = ms[1] = ms[2] = 0.f;
+  if (rc == KMPC_OK) {
+    for (int t = 0; t < T; ++t)
+      for (int k = 0; k < 3; ++k) {
+        float v = 0.f;
+        cudaEventElapsedTime(&v, ev[4 * t + k], ev[4 * t + k + 1]);
+        ms[k] += v;
+      }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
 }
 
 }  // extern "C"

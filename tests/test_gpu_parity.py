@@ -1,0 +1,280 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI (ctypes -> libkmpc.so),
+against the oracle and the reference goldens.  Run on the B200 box with `-m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import helpers as H
+import koopman_online_updated_mpc_b200 as K
+from oracle import closed_loop as ocl
+from oracle import edmd as oedmd
+from oracle import lift as olift
+from oracle import plant as oplant
+from oracle import rls as orls
+
+pytestmark = pytest.mark.gpu
+CUDA = H.CudaBackend()
+
+
+# ------------------------------------------------------------------------------ stage 1: lift --
+@pytest.mark.parametrize("system", ["duffing", "vdp", "tank"])
+def test_encoder_matches_oracle(system):
+    Ws, bs = H.oracle_weights(system)
+    enc = K.Encoder(Ws, bs)
+    rs = np.random.RandomState(0)
+    for S in (1, 31, 32, 33, 257, 4097):          # ragged tiles (kTileS = 32)
+        x = rs.uniform(-2.5, 2.5, (S, 2))
+        z = enc(x)
+        assert z.shape == (S, enc.nz)
+        np.testing.assert_allclose(z, olift.encoder_forward(Ws, bs, x), rtol=0, atol=1e-12)
+    from test_oracle_golden import KAT
+    for xk, zk in KAT[system].items():            # SURVEY Appendix A known answers
+        np.testing.assert_allclose(enc(np.array(xk)), zk, rtol=0, atol=2e-10)
+    assert enc(np.zeros((0, 2))).shape == (0, enc.nz)   # empty batch
+
+
+def test_encoder_lift_modes_and_tensor_kinds():
+    Ws, bs = H.oracle_weights("duffing")
+    enc = K.Encoder(Ws, bs)
+    x = np.random.RandomState(1).uniform(-2, 2, (100, 2))
+    for mode in (0, 1, 2):
+        np.testing.assert_allclose(enc(x, mode), olift.lift_mlp(Ws, bs, x, mode), rtol=0, atol=1e-12)
+    xt = torch.from_numpy(x)
+    assert isinstance(enc(xt), torch.Tensor) and not enc(xt).is_cuda
+    zc = enc(xt.cuda())
+    assert zc.is_cuda
+    np.testing.assert_allclose(zc.cpu().numpy(), enc(x), rtol=0, atol=0)
+
+
+def test_encoder_matches_reference_lifted_snapshots():
+    g = H.golden("ref_duffing.npz")
+    enc = K.Encoder.from_file(H.weights_path("duffing"))
+    np.testing.assert_allclose(enc(g["X_head"].T.copy()).T, g["PHIX_head"], rtol=0, atol=1e-12)
+
+
+def test_rbf_matches_oracle_and_reference():
+    cases.check_rbf(CUDA)
+
+
+# ------------------------------------------------------------------------------ stage 2: EDMD --
+def test_gram_and_edmd_match_oracle_and_reference_run():
+    g = H.golden("ref_duffing.npz")
+    Ws, bs = H.oracle_weights("duffing")
+    X, Y, U = oplant.generate_snapshots(100, 100, oplant.DUFFING_PRE, np.random.RandomState(101))
+    PHIX, PHIY = olift.encoder_forward(Ws, bs, X.T).T, olift.encoder_forward(Ws, bs, Y.T).T
+    A, B, C = K.edmd.edmd(PHIX, PHIY, U, X)          # reference call shape, numpy in / numpy out
+    np.testing.assert_allclose(A, g["A"], rtol=0, atol=1e-9)   # vs the reference script's own A, B, C
+    np.testing.assert_allclose(B, g["B"].reshape(8, 1), rtol=0, atol=1e-9)
+    np.testing.assert_allclose(C, g["C"], rtol=0, atol=1e-9)
+    pack = K.edmd.gram_accumulate(PHIX.T.copy(), PHIY.T.copy(), U.ravel(), X.T.copy()).cpu().numpy()
+    G, Aq, XV = oedmd.gram_pack(PHIX, PHIY, U, X)
+    np.testing.assert_allclose(pack[:-1], np.concatenate([G.ravel(), Aq.ravel(), XV.ravel()]), rtol=1e-12)
+    assert pack[-1] == 10000
+    # fused lift + Gram straight from raw snapshots, and the MATLAB joint-C variant
+    enc = K.Encoder(Ws, bs)
+    pack2 = K.edmd.gram_from_snapshots(enc, X.T.copy(), Y.T.copy(), U.ravel())
+    np.testing.assert_allclose(pack2.cpu().numpy(), pack, rtol=1e-11)
+    A2, B2, C2, st = K.edmd.edmd_solve(pack2, 8, 2, K.edmd.C_JOINT)
+    Ao, Bo, Co = oedmd.edmd_from_gram(G, Aq, XV, 8, oedmd.C_JOINT)
+    assert int(st.item()) == 0
+    np.testing.assert_allclose(C2.cpu().numpy(), Co, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(A2.cpu().numpy(), Ao, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("nz", [3, 10, 11])
+def test_gram_other_dimensions(nz):
+    rs = np.random.RandomState(nz)
+    M = 1237                                         # ragged: not a multiple of the block size
+    PX, PY, U, X = rs.randn(nz, M), rs.randn(nz, M), rs.randn(1, M), rs.randn(2, M)
+    pack = K.edmd.gram_accumulate(PX.T.copy(), PY.T.copy(), U.ravel(), X.T.copy()).cpu().numpy()
+    G, Aq, XV = oedmd.gram_pack(PX, PY, U, X)
+    np.testing.assert_allclose(pack[:-1], np.concatenate([G.ravel(), Aq.ravel(), XV.ravel()]), rtol=1e-11, atol=1e-11)
+    A, B, C = K.edmd.edmd(PX, PY, U, X)
+    Ao, Bo, Co = oedmd.edmd_pinv(PX, PY, U, X)
+    np.testing.assert_allclose(A, Ao, atol=1e-10)
+    np.testing.assert_allclose(C, Co, atol=1e-10)
+
+
+def test_edmd_rank_deficient_is_flagged():
+    rs = np.random.RandomState(0)
+    PX = rs.randn(8, 500)
+    PX[7] = PX[0]                                    # duplicate observable -> singular Gram
+    with pytest.raises(K.KmpcError):
+        K.edmd.edmd(PX, rs.randn(8, 500), rs.randn(1, 500), rs.randn(2, 500))
+
+
+# ------------------------------------------------------------------------------ stage 3: RLS ---
+@pytest.mark.parametrize("nz,lam,update_c,skip_first,p0,q0", [
+    (8, 1.0, True, False, 1e4, 100.0), (8, 1.0, True, False, 1e5, 1e5), (10, 0.98, True, False, 1e4, 1e4),
+    (10, 1.0, False, False, 1e4, 1e4), (10, 1.0, True, True, 1e4, 1e4), (16, 1.0, True, False, 1e3, 1e3),
+])
+def test_rls_matches_oracle(nz, lam, update_c, skip_first, p0, q0):
+    cases.check_rls(CUDA, nz, 2, lam, update_c, skip_first, p0, q0)
+
+
+def test_rls_duffing_trace_reproduces_reference_state():
+    """Teacher-forced on the reference's own (x_k, u_k) trace: after 300 updates the device RLS
+    state equals the K_A / inv_K_G / bar_X / bar_Q the reference script ended with."""
+    g = H.golden("ref_duffing.npz")
+    Ws, bs = H.oracle_weights("duffing")
+    enc = K.Encoder(Ws, bs)
+    Xg, Ug = g["logXloc"].T, g["logUloc"][0]
+    xs = np.concatenate([[[-2.0, -2.0]], Xg[:-1]])
+    Z, Yl = enc(xs), enc(Xg)
+    st = K.RLSState(1, 8, 2, 1e4, 100.0)
+    for k in range(300):
+        A, B, C = K.rls_update(st, Z[k:k + 1], Ug[k:k + 1], Yl[k:k + 1], Xg[k:k + 1])
+    np.testing.assert_allclose(st.KA[0].cpu().numpy(), g["K_A"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(st.P[0].cpu().numpy(), g["inv_K_G"], rtol=0, atol=1e-8 * np.abs(g["inv_K_G"]).max())
+    np.testing.assert_allclose(A[0].cpu().numpy(), g["Aloc"], rtol=0, atol=1e-5 * np.abs(g["Aloc"]).max())
+    np.testing.assert_allclose(C[0].cpu().numpy(), g["Cloc"], rtol=0, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------ stage 4: QP ----
+@pytest.mark.parametrize("nz,ny,N,kw", [
+    (8, 2, 10, {}), (8, 8, 10, dict(identity=True)), (11, 1, 20, {}), (8, 2, 50, dict(S=6)),
+    (8, 2, 10, dict(shared=True)), (8, 2, 10, dict(r_full=True)), (8, 2, 10, dict(terminal=True)),
+    (8, 8, 10, dict(identity=True, terminal=True)), (8, 2, 10, dict(wide=True)), (3, 1, 1, {}),
+    (16, 4, 64, dict(S=3)), (8, 2, 10, dict(S=1029)),
+])
+def test_qp_matches_oracle(nz, ny, N, kw):
+    cases.check_qp(CUDA, nz, ny, N, **kw)
+
+
+def test_qp_close_to_reference_lbfgsb():
+    cases.check_qp_vs_literal(CUDA)
+
+
+def test_plant_matches_oracle():
+    cases.check_plant(CUDA)
+
+
+# ------------------------------------------------------------------------------ fused loop -----
+def _run_cuda(case, T, x0=None, warm=None, **kw):
+    enc = K.Encoder(case["Ws"], case["bs"]) if case["Ws"] is not None else None
+    loop = K.ClosedLoop(case["spec"], case["x0"] if x0 is None else x0, case["A"], case["B"], case["C"],
+                        case["r"], encoder=enc, cx=case["cx"], rls_state=warm, log_steps=T, **kw)
+    loop.run(T)
+    torch.cuda.synchronize()
+    return dict(log_x=loop.log_x.cpu().numpy(), log_u=loop.log_u.cpu().numpy(), status=loop.status.cpu().numpy(),
+                A=loop.A.cpu().numpy(), B=loop.B.cpu().numpy(), C=loop.C.cpu().numpy(), loop=loop)
+
+
+@pytest.mark.parametrize("name,T", [("duffing", 150), ("duffing_frozen", 130), ("vdp", 150), ("vdp_frozen", 110),
+                                    ("duffing_rbf_frozen", 110)])
+def test_closed_loop_matches_oracle_and_reference(name, T):
+    case = cases.loop_case(name)
+    run = _run_cuda(case, T)
+    cases.compare_loop(run, cases.oracle_loops(case, T), "update" if case["update"] else "frozen", T)
+    gx, gu = case["gold"]           # scenario 0 == the reference script's own run from x0 = [-2,-2]
+    assert np.abs(run["log_x"][:, 0].T - gx[:, :T]).max() < 2e-4
+    enc = K.Encoder(case["Ws"], case["bs"]) if case["Ws"] is not None else None
+    loop2 = K.ClosedLoop(case["spec"], case["x0"], case["A"], case["B"], case["C"], case["r"], encoder=enc,
+                         cx=case["cx"], log_steps=T)
+    loop2.run(60).run(T - 60)       # chunked execution is bit-identical
+    assert np.array_equal(loop2.log_x.cpu().numpy(), run["log_x"])
+    assert loop2.step_index == T
+
+
+def test_vdp_closed_loop_vs_reference_golden_file():
+    """600 steps against VDP_Revise_2/NN_Encoder.mat (vanderpol.py:1112), update loop."""
+    nn = H.golden("vdp_nn_encoder_head.npz")
+    case = cases.loop_case("vdp")
+    run = _run_cuda(case, 600, x0=np.array([[-2.0, -2.0]]))
+    assert np.abs(run["log_x"][:, 0].T - nn["X_Collection"][:, :600]).max() < 1e-4
+    assert run["status"][0] == 0
+
+
+@pytest.mark.parametrize("name,x0", [("duffing", [1.91195805, 0.15398348]), ("vdp", [-2.0, -2.0])])
+def test_teacher_forced_single_steps_along_the_horizon(name, x0):
+    case = cases.loop_case(name)
+    batch, want = cases.teacher_forced_batch(case, np.array(x0), 300)
+    S = len(batch["x"])
+    warm = K.RLSState(S, 8, 2)
+    for k in ("KA", "P", "barX", "barQ"):
+        getattr(warm, k).copy_(torch.from_numpy(batch[k]))
+    enc = K.Encoder(case["Ws"], case["bs"])
+    loop = K.ClosedLoop(case["spec"], batch["x"], batch["A"], batch["B"], batch["C"], case["r"], encoder=enc,
+                        rls_state=warm, log_steps=1, params_pre=batch["params"], params_post=batch["params"],
+                        u_prev=batch["u_prev"])
+    loop.run(1)
+    got = dict(u=loop.log_u[0].cpu().numpy(), x=loop.log_x[0].cpu().numpy(), z=loop.z.cpu().numpy(),
+               A=loop.A.cpu().numpy(), B=loop.B.cpu().numpy(), C=loop.C.cpu().numpy())
+    cases.compare_teacher_forced(got, want)
+
+
+def test_closed_loop_rbf_warm_rls():
+    g = H.golden("ref_duffing_rbf.npz")
+    X, Y, U = oplant.generate_snapshots(100, 100, oplant.DUFFING_PRE, np.random.RandomState(101))
+    PX, PY = olift.rbf_lift(X.T, g["cx"]).T, olift.rbf_lift(Y.T, g["cx"]).T
+    G, Aq, XV = oedmd.gram_pack(PX, PY, U, X)
+    x0 = np.array([[-2.0, -2.0], [1.0, 0.5]])
+    T = 110
+    warm = K.RLSState.warm(2, G, Aq, XV[:, :8], G[:8, :8])
+    loop = K.ClosedLoop(K.rbf_spec(), x0, g["A"], g["B"], g["C"], np.array([1.0, 0.0]), cx=g["cx"],
+                        rls_state=warm, log_steps=T).run(T)
+    lx = loop.log_x.cpu().numpy()
+    cfg = ocl.rbf_config(g["cx"])
+    for s in range(2):
+        o = ocl.run_loop(cfg, g["A"], g["B"], g["C"], x0[s], T, update=ocl.UPDATE_RLS, qp="exact",
+                         warm=orls.RLSState.warm(G, Aq, XV[:, :8], G[:8, :8]))
+        assert np.abs(o["X"] - lx[:, s]).max() < 1e-7
+    assert np.abs(lx[:, 0].T - g["logXloc"][:, :T]).max() < 1e-4
+
+
+def test_closed_loop_tank_velocity_form():
+    t = cases.tank_setup()
+    x0 = np.array([[0.0, 0.0], [0.5, 1.5], [2.0, 0.2]])
+    T = 160
+    enc = K.Encoder(t["Ws"], t["bs"])
+    loop = K.ClosedLoop(K.tank_spec(), x0, t["A"], t["B"], t["C"], np.array([1.0]), encoder=enc, log_steps=T).run(T)
+    lx, lu = loop.log_x.cpu().numpy(), loop.log_u.cpu().numpy()
+    for s in range(len(x0)):
+        o = ocl.run_loop(t["cfg"], t["A"], t["B"], t["C"], x0[s], T, update=ocl.UPDATE_RLS, qp="exact")
+        assert np.abs(o["X"] - lx[:, s]).max() < 5e-3, s
+        assert np.abs(o["X"][60:100] - lx[60:100, s]).max() < 1e-5, s
+    du = np.abs(np.diff(np.concatenate([np.zeros((1, len(x0))), lu]), axis=0))
+    assert du.max() <= 0.5 + 1e-9 and np.abs(lu).max() <= 8.0 + 1e-9 and lx.min() >= 0.0
+
+
+# ------------------------------------------------------------------------------ full size ------
+def test_full_size_vdp_properties_and_shard_invariance():
+    """BASELINE config 2 shape (4096 VDP scenarios, tracking + online update): size-independent
+    properties -- bounds respected, finite, status clean, per-scenario results bit-identical
+    whether the batch runs whole or as two shards (scenarios are independent)."""
+    Ws, bs = H.oracle_weights("vdp")
+    g = H.golden("ref_vanderpol.npz")
+    enc = K.Encoder(Ws, bs)
+    rs = np.random.default_rng(20240601)
+    S, T = 4096, 60
+    x0 = rs.uniform(-2, 2, (S, 2))
+    x0[0] = [-2.0, -2.0]
+    xref = np.stack([rs.uniform(-1, 1, S), np.zeros(S)], axis=1)
+    xref[0] = [1.0, 0.0]
+    r = enc(xref)
+    spec = K.vanderpol_spec()
+
+    def run(sl):
+        loop = K.ClosedLoop(spec, x0[sl], g["A"], g["B"], g["C"], r[sl], encoder=enc, log_steps=T).run(T)
+        torch.cuda.synchronize()
+        return loop.log_x.cpu().numpy(), loop.log_u.cpu().numpy(), loop.status.cpu().numpy(), loop.A.cpu().numpy()
+
+    lx, lu, st, A = run(slice(0, S))
+    assert np.all(np.isfinite(lx)) and np.all(np.isfinite(A)) and np.all(st == 0)
+    assert lu.min() >= -6.0 and lu.max() <= 6.0
+    assert np.abs(lx[:, 0].T - g["logXloc"][:, :T]).max() < 1e-4     # scenario 0 is the reference's own
+    lx1, lu1, _, A1 = run(slice(0, S // 2))
+    lx2, lu2, _, A2 = run(slice(S // 2, S))
+    assert np.array_equal(np.concatenate([lx1, lx2], axis=1), lx)
+    assert np.array_equal(np.concatenate([lu1, lu2], axis=1), lu)
+    assert np.array_equal(np.concatenate([A1, A2], axis=0), A)
+    o = ocl.run_loop(ocl.vanderpol_config(Ws, bs, xref[77]), g["A"], g["B"], g["C"], x0[77], T,
+                     update=ocl.UPDATE_RLS, qp="exact")
+    assert np.abs(o["X"] - lx[:, 77]).max() < 1e-4                    # a random scenario vs the oracle
+
+
+def test_launch_counter_counts_kernels():
+    before = K.launch_count()
+    K.lift.rbf(np.zeros((4, 2)), np.ones((8, 2)))
+    assert K.launch_count() == before + 1
