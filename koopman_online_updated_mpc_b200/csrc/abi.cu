@@ -8,6 +8,7 @@ std::atomic<int64_t> g_launches{0};
 static thread_local char g_err[512] = "";
 int record_cuda_error(cudaError_t e, const char* what, const char* file, int line) {
   snprintf(g_err, sizeof(g_err), "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+  cudaGetLastError();  // clear the (non-sticky) last-error slot so later launches are not blamed
   return KMPC_ERR_CUDA;
 }
 }  // namespace kmpc

@@ -13,24 +13,85 @@
 
 namespace kmpc {
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+constexpr int kLoopThreads = 128;
+
+// G lanes per scenario; NZ/N/OUT/DU > 0 give a compile-time QP shape (loops unrolled, indices
+// folded), NZ == 0 reads the shape from the config at run time.
+template <int G, int NZ, int N, int OUT, int DU>
+__global__ void __launch_bounds__(kLoopThreads)
 loop_qp_plant_kernel(LoopDev d, int64_t step, int64_t log_slot) {
   extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5;
-  const int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  if (s >= d.c.S) return;
-  const bool identity = d.c.out_mode == KMPC_OUT_IDENTITY;
-  loop_qp_plant_scenario(d, s, step, log_slot,
-                         smem + (size_t)warp * qp_ws_doubles(loop_nzq(d.c), loop_ny(d.c), d.c.N, identity));
+  const int group = threadIdx.x / G;
+  int64_t s = (int64_t)blockIdx.x * (blockDim.x / G) + group;
+  const bool valid = s < d.c.S;
+  if (!valid) s = d.c.S - 1;
+  LoopShape sh;
+  if (NZ > 0) {
+    sh.nz = NZ; sh.N = N; sh.out_mode = OUT; sh.du_aug = DU;
+  } else {
+    sh = loop_shape(d.c);
+  }
+  const int nzq = sh.nz + sh.du_aug;
+  const bool identity = sh.out_mode == KMPC_OUT_IDENTITY;
+  const int ny = identity ? nzq : (sh.out_mode == KMPC_OUT_C ? 2 : 1);
+  loop_qp_plant_scenario<G>(d, sh, s, valid, step, log_slot,
+                            smem + (size_t)group * qp_ws_doubles(nzq, ny, sh.N, identity));
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+template <int G, int NZ>
+__global__ void __launch_bounds__(kLoopThreads)
 loop_rls_kernel(LoopDev d, int first) {
   extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5;
-  const int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  if (s >= d.c.S) return;
-  loop_rls_scenario(d, s, first, smem + (size_t)warp * rls_ws_doubles(d.c.nz, d.c.n));
+  const int group = threadIdx.x / G;
+  int64_t s = (int64_t)blockIdx.x * (blockDim.x / G) + group;
+  const bool valid = s < d.c.S;
+  if (!valid) s = d.c.S - 1;
+  const int nz = NZ > 0 ? NZ : d.c.nz;
+  loop_rls_scenario<G>(d, nz, s, valid, first, smem + (size_t)group * rls_ws_doubles(nz, 2));
+}
+
+typedef void (*QpKernel)(LoopDev, int64_t, int64_t);
+typedef void (*RlsKernel)(LoopDev, int);
+struct LoopLaunch {
+  QpKernel qp;
+  RlsKernel rls;
+  int qp_g, rls_g;          // lanes per scenario
+  int qp_spb, rls_spb;      // scenarios per block
+  int qp_smem, rls_smem;    // dynamic shared memory per block (bytes)
+};
+
+static bool select_launch(const kmpc_loop_config& c, LoopLaunch* L) {
+  const int nzq = c.nz + (c.du_aug ? 1 : 0);
+  const bool identity = c.out_mode == KMPC_OUT_IDENTITY;
+  const int ny = identity ? nzq : (c.out_mode == KMPC_OUT_C ? 2 : 1);
+  L->qp_g = 32;
+  if (c.nz == 8 && c.N == 10 && !c.du_aug && c.out_mode == KMPC_OUT_IDENTITY) {
+    L->qp = loop_qp_plant_kernel<16, 8, 10, KMPC_OUT_IDENTITY, 0>;   // vanderpol.py
+    L->qp_g = 16;
+  } else if (c.nz == 8 && c.N == 10 && !c.du_aug && c.out_mode == KMPC_OUT_C) {
+    L->qp = loop_qp_plant_kernel<16, 8, 10, KMPC_OUT_C, 0>;          // duffing.py, duffing_RBF.py
+    L->qp_g = 16;
+  } else if (c.nz == 10 && c.N == 20 && c.du_aug && c.out_mode == KMPC_OUT_C_ROW) {
+    L->qp = loop_qp_plant_kernel<32, 10, 20, KMPC_OUT_C_ROW, 1>;     // Tank_System.m
+  } else if (c.nz == 8 && c.N == 50 && !c.du_aug && c.out_mode == KMPC_OUT_C) {
+    L->qp = loop_qp_plant_kernel<32, 8, 50, KMPC_OUT_C, 0>;          // BASELINE config 5
+  } else {
+    L->qp = loop_qp_plant_kernel<32, 0, 0, 0, 0>;
+  }
+  L->rls_g = 32;
+  if (c.nz == 8) L->rls = loop_rls_kernel<32, 8>;
+  else if (c.nz == 10) L->rls = loop_rls_kernel<32, 10>;
+  else L->rls = loop_rls_kernel<32, 0>;
+  const int budget = 200 * 1024;
+  const int qp_ws = qp_ws_doubles(nzq, ny, c.N, identity) * (int)sizeof(double);
+  const int rls_ws = rls_ws_doubles(c.nz, 2) * (int)sizeof(double);
+  L->qp_spb = kLoopThreads / L->qp_g;
+  while (L->qp_spb > 1 && L->qp_spb * qp_ws > budget) L->qp_spb >>= 1;
+  L->rls_spb = kLoopThreads / L->rls_g;
+  while (L->rls_spb > 1 && L->rls_spb * rls_ws > budget) L->rls_spb >>= 1;
+  L->qp_smem = L->qp_spb * qp_ws;
+  L->rls_smem = L->rls_spb * rls_ws;
+  return L->qp_smem <= budget && L->rls_smem <= budget;
 }
 
 }  // namespace kmpc
@@ -42,7 +103,7 @@ struct kmpc_ctx {
   const kmpc_encoder* enc;
   int64_t step;
   int rls_started;
-  int qp_smem, rls_smem;
+  LoopLaunch launch;
 };
 
 extern "C" {
@@ -80,10 +141,6 @@ int kmpc_ctx_create(kmpc_ctx** out, const kmpc_loop_config* cfg, const kmpc_loop
   ctx->enc = enc;
   ctx->step = 0;
   ctx->rls_started = rls_started;
-  const bool identity = c.out_mode == KMPC_OUT_IDENTITY;
-  const int ny = identity ? nzq : (c.out_mode == KMPC_OUT_C ? c.n : 1);
-  ctx->qp_smem = kWarpsPerBlock * qp_ws_doubles(nzq, ny, c.N, identity) * (int)sizeof(double);
-  ctx->rls_smem = kWarpsPerBlock * rls_ws_doubles(c.nz, c.n) * (int)sizeof(double);
   ctx->d.z_next = nullptr;
   ctx->d.x_prev = nullptr;
   if (cudaMalloc(&ctx->d.z_next, (size_t)c.S * c.nz * sizeof(double)) != cudaSuccess ||
@@ -91,8 +148,13 @@ int kmpc_ctx_create(kmpc_ctx** out, const kmpc_loop_config* cfg, const kmpc_loop
     kmpc_ctx_destroy(ctx);
     return KMPC_ERR_ALLOC;
   }
-  if (ensure_smem(loop_qp_plant_kernel, ctx->qp_smem) != cudaSuccess ||
-      ensure_smem(loop_rls_kernel, ctx->rls_smem) != cudaSuccess) {
+  if (!select_launch(c, &ctx->launch)) {
+    kmpc_ctx_destroy(ctx);
+    return KMPC_ERR_UNSUPPORTED;
+  }
+  if (ensure_smem(ctx->launch.qp, ctx->launch.qp_smem) != cudaSuccess ||
+      ensure_smem(ctx->launch.rls, ctx->launch.rls_smem) != cudaSuccess) {
+    cudaGetLastError();
     kmpc_ctx_destroy(ctx);
     return KMPC_ERR_CUDA;
   }
@@ -115,10 +177,12 @@ int64_t kmpc_ctx_step_index(const kmpc_ctx* ctx) { return ctx ? ctx->step : -1; 
 static int run_one_step(kmpc_ctx* ctx, void* stream, cudaEvent_t* ev) {
   cudaStream_t st = as_stream(stream);
   const kmpc_loop_config& c = ctx->d.c;
-  const unsigned grid = (unsigned)((c.S + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const LoopLaunch& L = ctx->launch;
+  const unsigned qp_grid = (unsigned)((c.S + L.qp_spb - 1) / L.qp_spb);
+  const unsigned rls_grid = (unsigned)((c.S + L.rls_spb - 1) / L.rls_spb);
   const int64_t slot = (ctx->step < ctx->d.b.log_capacity) ? ctx->step : -1;
   if (ev) KMPC_CUDA(cudaEventRecord(ev[0], st));
-  loop_qp_plant_kernel<<<grid, kWarpsPerBlock * 32, ctx->qp_smem, st>>>(ctx->d, ctx->step, slot);
+  L.qp<<<qp_grid, L.qp_spb * L.qp_g, L.qp_smem, st>>>(ctx->d, ctx->step, slot);
   KMPC_AFTER_LAUNCH();
   if (ev) KMPC_CUDA(cudaEventRecord(ev[1], st));
   // lift(x+): into z_next when the RLS still needs the old z, else straight into z
@@ -131,7 +195,7 @@ static int run_one_step(kmpc_ctx* ctx, void* stream, cudaEvent_t* ev) {
   if (rc != KMPC_OK) return rc;
   if (ev) KMPC_CUDA(cudaEventRecord(ev[2], st));
   if (c.update) {
-    loop_rls_kernel<<<grid, kWarpsPerBlock * 32, ctx->rls_smem, st>>>(ctx->d, ctx->rls_started ? 0 : 1);
+    L.rls<<<rls_grid, L.rls_spb * L.rls_g, L.rls_smem, st>>>(ctx->d, ctx->rls_started ? 0 : 1);
     KMPC_AFTER_LAUNCH();
     ctx->rls_started = 1;
   }

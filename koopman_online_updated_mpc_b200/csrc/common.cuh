@@ -40,4 +40,12 @@ inline cudaError_t ensure_smem(K kernel, int bytes) {
 
 constexpr int kWarpsPerBlock = 4;
 
+// how many warps (each with `doubles_per_warp` of workspace) fit in a block's shared memory
+inline int warps_that_fit(int doubles_per_warp) {
+  const int budget = 200 * 1024;
+  int w = kWarpsPerBlock;
+  while (w > 1 && w * doubles_per_warp * (int)sizeof(double) > budget) w >>= 1;
+  return (w * doubles_per_warp * (int)sizeof(double) <= budget) ? w : 0;
+}
+
 }  // namespace kmpc

@@ -122,8 +122,8 @@ __global__ void edmd_solve_kernel(const double* __restrict__ pack, int nz, int n
   for (int e = lane; e < nz * nz; e += 32) G2[e] = pack[(e / nz) * nv + (e % nz)];
   for (int e = lane; e < n * nz; e += 32) R2[e] = pack[nv * nv + nz * nv + (e / nz) * nv + (e % nz)];
   __syncwarp();
-  int st = spd_right_solve_warp(G, nv, R, nz + n);   // [A B; Cj *] = [Aq; XV] G^-1
-  if (c_variant == KMPC_C_PYTHON) st |= spd_right_solve_warp(G2, nz, R2, n);
+  int st = spd_right_solve_warp<32>(G, nv, R, nz + n);   // [A B; Cj *] = [Aq; XV] G^-1
+  if (c_variant == KMPC_C_PYTHON) st |= spd_right_solve_warp<32>(G2, nz, R2, n);
   for (int e = lane; e < nz * nv; e += 32) {
     const int i = e / nv, j = e - i * nv;
     if (j < nz) A[i * nz + j] = R[e];
@@ -149,9 +149,9 @@ int64_t kmpc_gram_pack_len(int nz, int n) {
 
 int kmpc_gram_accumulate(const double* psi, const double* psi_next, const double* u,
                          const double* x, int64_t M, int nz, int n, double* pack, void* stream) {
-  if (!psi || !psi_next || !u || !x || !pack || M < 0) return KMPC_ERR_ARG;
-  if (nz < 1 || nz > KMPC_MAX_NZ || n < 1 || n > 4) return KMPC_ERR_ARG;
+  if (nz < 1 || nz > KMPC_MAX_NZ || n < 1 || n > 4 || M < 0) return KMPC_ERR_ARG;
   if (M == 0) return KMPC_OK;
+  if (!psi || !psi_next || !u || !x || !pack) return KMPC_ERR_ARG;
   cudaStream_t st = as_stream(stream);
   int dev = 0, sms = 148;
   KMPC_CUDA(cudaGetDevice(&dev));

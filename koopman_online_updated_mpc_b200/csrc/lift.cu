@@ -3,12 +3,16 @@
 // Reference: duffing.py:21-29 (`nn.Sequential(Linear(2,100), ReLU, Linear(100,100), ReLU,
 // Linear(100,100), ReLU, Linear(100,8))`), Encoder_Tank.m:3-5 (3 layers, nz = 10).
 //
-// Layout: one CTA lifts a tile of kTileS = 32 scenarios through ALL layers; activations stay in
+// Layout: one CTA lifts tiles of kTileS = 32 scenarios through ALL layers; activations stay in
 // shared memory, k-major ([k][scenario]) so a thread's 4 consecutive scenarios are one 32-byte
 // read that is broadcast to the 4 lanes sharing the row group.  Weights are stored transposed and
-// padded ([in][out_pad], out_pad multiple of 4) in global memory and read through L1 (all CTAs
-// read the same 170 KB, so they are L1/L2 hits).  Each thread owns a 4 (scenarios) x 4 (outputs)
-// register tile: 16 DFMA per 4 shared + 4 global 8-byte loads.
+// padded ([in][out_pad], out_pad multiple of 4), packed layer after layer in one device buffer.
+// Each thread owns a 4 (scenarios) x 4 (outputs) register tile: 16 DFMA per 8 x 8-byte operands.
+//
+// encoder_smem_kernel (default): the whole packed weight set (171 KB for 2-100-100-100-8) is
+// brought into shared memory ONCE per CTA by the TMA engine (cp.async.bulk, one mbarrier per
+// layer so layer 1 starts while layers 2.. are still in flight); CTAs are persistent over tiles.
+// encoder_kernel (fallback for nets that do not fit 227 KB): weights read from global/L2.
 #include <vector>
 
 #include "common.cuh"
@@ -26,12 +30,193 @@ struct EncParams {
   const double* wt[KMPC_MAX_LAYERS];
   const double* b[KMPC_MAX_LAYERS];
   const double* z0;
+  const double* packed;            // [W1t | b1 | W2t | b2 | ...] (same layout as the smem copy)
+  int woff[KMPC_MAX_LAYERS];       // offset (doubles) of layer l's W block inside `packed`
+  int wlen[KMPC_MAX_LAYERS];       // doubles of layer l's W + bias block
+  int total_w;                     // doubles in `packed`
+  int actw;                        // activation buffer width (max padded layer width)
 };
+
+// ---- TMA bulk-copy / mbarrier helpers (PTX; SASS: UBLKCP, SYNCS) --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// One layer of the 4x4 register-tiled GEMM for this thread: acc = bias + act_in^T W.
+// WT_LD: functor-free: weights read with plain loads from `wt` (shared or global pointer).
+template <bool kGlobalWeights>
+__device__ __forceinline__ void enc_layer_tile(const double* __restrict__ hp, const double* __restrict__ wp,
+                                               const double* __restrict__ bias4, int in, int outp,
+                                               double (&acc)[4][4]) {
+  double2 b01, b23;
+  if (kGlobalWeights) {
+    b01 = __ldg(reinterpret_cast<const double2*>(bias4));
+    b23 = __ldg(reinterpret_cast<const double2*>(bias4 + 2));
+  } else {
+    b01 = *reinterpret_cast<const double2*>(bias4);
+    b23 = *reinterpret_cast<const double2*>(bias4 + 2);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    acc[r][0] = b01.x;
+    acc[r][1] = b01.y;
+    acc[r][2] = b23.x;
+    acc[r][3] = b23.y;
+  }
+#pragma unroll 4
+  for (int k = 0; k < in; ++k) {
+    const double2 h01 = *reinterpret_cast<const double2*>(hp + k * kTileS);
+    const double2 h23 = *reinterpret_cast<const double2*>(hp + k * kTileS + 2);
+    double2 w01, w23;
+    if (kGlobalWeights) {
+      w01 = __ldg(reinterpret_cast<const double2*>(wp + (size_t)k * outp));
+      w23 = __ldg(reinterpret_cast<const double2*>(wp + (size_t)k * outp + 2));
+    } else {
+      w01 = *reinterpret_cast<const double2*>(wp + k * outp);
+      w23 = *reinterpret_cast<const double2*>(wp + k * outp + 2);
+    }
+    const double h[4] = {h01.x, h01.y, h23.x, h23.y};
+    const double w[4] = {w01.x, w01.y, w23.x, w23.y};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = fma(h[r], w[c], acc[r][c]);
+  }
+}
+
+// ReLU + store to the next activation buffer, or final store to global z.
+__device__ __forceinline__ void enc_store_tile(const double (&acc)[4][4], bool last, double* act_out, int cg,
+                                               int rg, double* __restrict__ z, int64_t row0, int64_t S,
+                                               int out, int out_dim, int off, int lift_mode,
+                                               const double* __restrict__ z0) {
+  if (!last) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double2 o01, o23;
+      o01.x = fmax(acc[0][c], 0.0);
+      o01.y = fmax(acc[1][c], 0.0);
+      o23.x = fmax(acc[2][c], 0.0);
+      o23.y = fmax(acc[3][c], 0.0);
+      double* op = act_out + (4 * cg + c) * kTileS + 4 * rg;
+      *reinterpret_cast<double2*>(op) = o01;
+      *reinterpret_cast<double2*>(op + 2) = o23;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t row = row0 + 4 * rg + r;
+      if (row < S) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col = 4 * cg + c;
+          if (col < out) {
+            double v = acc[r][c];
+            if (lift_mode != KMPC_LIFT_RAW) v -= z0[col];
+            z[row * out_dim + off + col] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Persistent CTAs, weights resident in shared memory (loaded once by TMA bulk copies).
+__global__ void __launch_bounds__(kEncThreads, 1)
+encoder_smem_kernel(EncParams p, const double* __restrict__ x, double* __restrict__ z, int64_t S,
+                    int lift_mode, int out_dim, int64_t num_tiles) {
+  extern __shared__ __align__(16) double smem[];
+  double* act_in = smem;
+  double* act_out = smem + p.actw * kTileS;
+  double* wsm = smem + 2 * p.actw * kTileS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + p.total_w);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int l = 0; l < p.n_layers; ++l) mbar_init(&bars[l], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int l = 0; l < p.n_layers; ++l) {
+      const uint32_t bytes = (uint32_t)p.wlen[l] * 8u;
+      mbar_expect_tx(&bars[l], bytes);
+      for (uint32_t o = 0; o < bytes; o += 32768u) {
+        const uint32_t sz = (bytes - o < 32768u) ? (bytes - o) : 32768u;
+        bulk_copy_g2s(reinterpret_cast<char*>(wsm + p.woff[l]) + o,
+                      reinterpret_cast<const char*>(p.packed + p.woff[l]) + o, sz, &bars[l]);
+      }
+    }
+  }
+  const int n = p.dims[0];
+  const int rg = lane & 7, cgl = lane >> 3;
+  const int off = (lift_mode == KMPC_LIFT_STACK) ? n : 0;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kTileS;
+    for (int e = tid; e < kTileS * n; e += kEncThreads) {
+      const int r = e / n, k = e - r * n;
+      const double v = (row0 + r < S) ? x[(row0 + r) * n + k] : 0.0;
+      act_in[k * kTileS + r] = v;
+      if (lift_mode == KMPC_LIFT_STACK && row0 + r < S) z[(row0 + r) * out_dim + k] = v;
+    }
+    __syncthreads();
+    for (int l = 0; l < p.n_layers; ++l) {
+      const int in = p.dims[l], outp = p.pad[l + 1], out = p.dims[l + 1];
+      const int ncg = outp >> 2;
+      const bool last = (l == p.n_layers - 1);
+      mbar_wait(&bars[l], 0);  // layer l's weights have landed (returns at once after the first tile)
+      const double* wt = wsm + p.woff[l];
+      const double* bias = wt + in * outp;
+      for (int cg0 = 0; cg0 < ncg; cg0 += kEncWarps * 4) {
+        const int cg = cg0 + warp * 4 + cgl;
+        if (cg < ncg) {
+          double acc[4][4];
+          enc_layer_tile<false>(act_in + 4 * rg, wt + 4 * cg, bias + 4 * cg, in, outp, acc);
+          enc_store_tile(acc, last, act_out, cg, rg, z, row0, S, out, out_dim, off, lift_mode, p.z0);
+        }
+      }
+      __syncthreads();
+      double* t = act_in;
+      act_in = act_out;
+      act_out = t;
+    }
+  }
+}
+
 
 __global__ void __launch_bounds__(kEncThreads)
 encoder_kernel(EncParams p, const double* __restrict__ x, double* __restrict__ z, int64_t S,
                int lift_mode, int out_dim) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   double* act_in = smem;
   double* act_out = smem + KMPC_MAX_WIDTH * kTileS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -50,67 +235,12 @@ encoder_kernel(EncParams p, const double* __restrict__ x, double* __restrict__ z
     const int in = p.dims[l], outp = p.pad[l + 1], out = p.dims[l + 1];
     const int ncg = outp >> 2;
     const bool last = (l == p.n_layers - 1);
-    const double* __restrict__ wt = p.wt[l];
-    const double* __restrict__ bias = p.b[l];
     for (int cg0 = 0; cg0 < ncg; cg0 += kEncWarps * 4) {
       const int cg = cg0 + warp * 4 + cgl;
       if (cg < ncg) {
         double acc[4][4];
-        {
-          const double2 b01 = __ldg(reinterpret_cast<const double2*>(bias + 4 * cg));
-          const double2 b23 = __ldg(reinterpret_cast<const double2*>(bias + 4 * cg + 2));
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            acc[r][0] = b01.x;
-            acc[r][1] = b01.y;
-            acc[r][2] = b23.x;
-            acc[r][3] = b23.y;
-          }
-        }
-        const double* hp = act_in + 4 * rg;
-        const double* wp = wt + 4 * cg;
-#pragma unroll 4
-        for (int k = 0; k < in; ++k) {
-          const double2 h01 = *reinterpret_cast<const double2*>(hp + k * kTileS);
-          const double2 h23 = *reinterpret_cast<const double2*>(hp + k * kTileS + 2);
-          const double2 w01 = __ldg(reinterpret_cast<const double2*>(wp + (size_t)k * outp));
-          const double2 w23 = __ldg(reinterpret_cast<const double2*>(wp + (size_t)k * outp + 2));
-          const double h[4] = {h01.x, h01.y, h23.x, h23.y};
-          const double w[4] = {w01.x, w01.y, w23.x, w23.y};
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = fma(h[r], w[c], acc[r][c]);
-        }
-        if (!last) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            double2 o01, o23;
-            o01.x = fmax(acc[0][c], 0.0);
-            o01.y = fmax(acc[1][c], 0.0);
-            o23.x = fmax(acc[2][c], 0.0);
-            o23.y = fmax(acc[3][c], 0.0);
-            double* op = act_out + (4 * cg + c) * kTileS + 4 * rg;
-            *reinterpret_cast<double2*>(op) = o01;
-            *reinterpret_cast<double2*>(op + 2) = o23;
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int64_t row = row0 + 4 * rg + r;
-            if (row < S) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const int col = 4 * cg + c;
-                if (col < out) {
-                  double v = acc[r][c];
-                  if (lift_mode != KMPC_LIFT_RAW) v -= p.z0[col];
-                  z[row * out_dim + off + col] = v;
-                }
-              }
-            }
-          }
-        }
+        enc_layer_tile<true>(act_in + 4 * rg, p.wt[l] + 4 * cg, p.b[l] + 4 * cg, in, outp, acc);
+        enc_store_tile(acc, last, act_out, cg, rg, z, row0, S, out, out_dim, off, lift_mode, p.z0);
       }
     }
     __syncthreads();
@@ -126,6 +256,8 @@ using namespace kmpc;
 
 struct kmpc_encoder {
   EncParams p;
+  int smem_bytes = 0;      // dynamic smem of encoder_smem_kernel (0: does not fit, use fallback)
+  int num_sms = 148;
   std::vector<double*> owned;
   double* d_z0 = nullptr;
   // L2-resident lift workspace for kmpc_gram_from_snapshots (allocated on first use)
@@ -135,12 +267,18 @@ struct kmpc_encoder {
 
 static int launch_encoder(const kmpc_encoder* enc, const double* x, double* z, int64_t S,
                           int lift_mode, cudaStream_t st) {
-  const int smem = 2 * KMPC_MAX_WIDTH * kTileS * (int)sizeof(double);
-  KMPC_CUDA(ensure_smem(encoder_kernel, smem));
   const int64_t tiles = (S + kTileS - 1) / kTileS;
   if (tiles > 0x7fffffff) return KMPC_ERR_ARG;
   const int out_dim = kmpc_encoder_out_dim(enc, lift_mode);
-  encoder_kernel<<<(unsigned)tiles, kEncThreads, smem, st>>>(enc->p, x, z, S, lift_mode, out_dim);
+  if (enc->smem_bytes > 0) {
+    KMPC_CUDA(ensure_smem(encoder_smem_kernel, enc->smem_bytes));
+    const unsigned grid = (unsigned)(tiles < enc->num_sms ? tiles : enc->num_sms);
+    encoder_smem_kernel<<<grid, kEncThreads, enc->smem_bytes, st>>>(enc->p, x, z, S, lift_mode, out_dim, tiles);
+  } else {
+    const int smem = 2 * KMPC_MAX_WIDTH * kTileS * (int)sizeof(double);
+    KMPC_CUDA(ensure_smem(encoder_kernel, smem));
+    encoder_kernel<<<(unsigned)tiles, kEncThreads, smem, st>>>(enc->p, x, z, S, lift_mode, out_dim);
+  }
   KMPC_AFTER_LAUNCH();
   return KMPC_OK;
 }
@@ -164,24 +302,43 @@ int kmpc_encoder_create(kmpc_encoder** out, const double* const* W, const double
     kmpc_encoder_destroy(enc);
     return code;
   };
+  // pack [W1t | b1 | W2t | b2 | ...]: transposed, output-padded, exactly the smem layout
+  std::vector<double> packed;
+  int actw = 4;
   for (int l = 0; l < n_layers; ++l) {
     const int in = dims[l], o = dims[l + 1], op = enc->p.pad[l + 1];
-    std::vector<double> wt((size_t)in * op, 0.0), bp(op, 0.0);
+    enc->p.woff[l] = (int)packed.size();
+    enc->p.wlen[l] = in * op + op;
+    packed.resize(packed.size() + (size_t)in * op + op, 0.0);
+    double* wt = packed.data() + enc->p.woff[l];
+    double* bp = wt + (size_t)in * op;
     for (int i = 0; i < o; ++i) {
       bp[i] = b[l][i];
       for (int k = 0; k < in; ++k) wt[(size_t)k * op + i] = W[l][(size_t)i * in + k];
     }
-    double *dw = nullptr, *db = nullptr;
-    if (cudaMalloc(&dw, wt.size() * sizeof(double)) != cudaSuccess) return fail(KMPC_ERR_ALLOC);
-    enc->owned.push_back(dw);
-    if (cudaMalloc(&db, bp.size() * sizeof(double)) != cudaSuccess) return fail(KMPC_ERR_ALLOC);
-    enc->owned.push_back(db);
-    // pageable-source async copies complete w.r.t. the host before returning
-    if (cudaMemcpyAsync(dw, wt.data(), wt.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess ||
-        cudaMemcpyAsync(db, bp.data(), bp.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess)
-      return fail(KMPC_ERR_CUDA);
-    enc->p.wt[l] = dw;
-    enc->p.b[l] = db;
+    if (enc->p.pad[l] > actw) actw = enc->p.pad[l];
+    if (l + 1 < n_layers && op > actw) actw = op;
+  }
+  enc->p.total_w = (int)packed.size();
+  enc->p.actw = actw;
+  double* dpk = nullptr;
+  if (cudaMalloc(&dpk, packed.size() * sizeof(double)) != cudaSuccess) return fail(KMPC_ERR_ALLOC);
+  enc->owned.push_back(dpk);
+  // pageable-source async copies complete w.r.t. the host before returning
+  if (cudaMemcpyAsync(dpk, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return fail(KMPC_ERR_CUDA);
+  enc->p.packed = dpk;
+  for (int l = 0; l < n_layers; ++l) {
+    enc->p.wt[l] = dpk + enc->p.woff[l];
+    enc->p.b[l] = dpk + enc->p.woff[l] + (size_t)dims[l] * enc->p.pad[l + 1];
+  }
+  {
+    int dev = 0, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&enc->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const size_t need = ((size_t)2 * actw * kTileS + packed.size()) * sizeof(double) + KMPC_MAX_LAYERS * 8;
+    enc->smem_bytes = (need <= (size_t)max_smem) ? (int)need : 0;
   }
   // theta(0) for the OFFSET / STACK lift modes (Koopman_update.m:67)
   double* scratch = nullptr;
@@ -214,9 +371,10 @@ int kmpc_encoder_out_dim(const kmpc_encoder* enc, int lift_mode) {
 
 int kmpc_encode(const kmpc_encoder* enc, const double* x, double* z, int64_t S, int lift_mode,
                 void* stream) {
-  if (!enc || !x || !z || S < 0) return KMPC_ERR_ARG;
+  if (!enc || S < 0) return KMPC_ERR_ARG;
   if (lift_mode < KMPC_LIFT_RAW || lift_mode > KMPC_LIFT_STACK) return KMPC_ERR_ARG;
   if (S == 0) return KMPC_OK;
+  if (!x || !z) return KMPC_ERR_ARG;
   return launch_encoder(enc, x, z, S, lift_mode, as_stream(stream));
 }
 

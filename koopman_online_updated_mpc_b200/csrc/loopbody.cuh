@@ -18,14 +18,26 @@ KMPC_HD inline int loop_ny(const kmpc_loop_config& c) {
   return c.out_mode == KMPC_OUT_IDENTITY ? loop_nzq(c) : (c.out_mode == KMPC_OUT_C ? c.n : 1);
 }
 
-// QP + plant for scenario s at closed-loop step `step`; `base` = this warp's smem slice.
-KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, int64_t s, int64_t step, int64_t log_slot,
-                                     double* base) {
+// Shape of the QP a loop solves; passed explicitly (not read from the config) so that kernel
+// instantiations with compile-time shapes get their loops unrolled and indices folded.
+struct LoopShape {
+  int nz, N, out_mode, du_aug;
+};
+KMPC_HD inline LoopShape loop_shape(const kmpc_loop_config& c) {
+  LoopShape sh = {c.nz, c.N, c.out_mode, c.du_aug ? 1 : 0};
+  return sh;
+}
+
+// QP + plant for scenario s at closed-loop step `step`; `base` = this group's smem slice;
+// `valid` = false for the padding groups of the last warp (compute, but write nothing).
+template <int G>
+KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, const LoopShape sh, int64_t s, bool valid,
+                                     int64_t step, int64_t log_slot, double* base) {
   const kmpc_loop_config& c = d.c;
-  const int nz = c.nz, n = c.n, N = c.N;
-  const int nzq = loop_nzq(c);
-  const bool identity = c.out_mode == KMPC_OUT_IDENTITY;
-  const int ny = loop_ny(c);
+  const int nz = sh.nz, n = 2, N = sh.N;
+  const int nzq = nz + sh.du_aug;
+  const bool identity = sh.out_mode == KMPC_OUT_IDENTITY;
+  const int ny = identity ? nzq : (sh.out_mode == KMPC_OUT_C ? n : 1);
   QpWs ws = qp_ws_carve(base, nzq, ny, N, identity);
   const int64_t sm = c.shared_model ? 0 : s;
   const double* A = d.b.A + sm * nz * nz;
@@ -47,13 +59,13 @@ KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, int64_t s, int64_t step, 
   if (!identity) {
     KMPC_LANE_LOOP(e, ny * nzq) {
       const int i = e / nzq, j = e - i * nzq;
-      const int row = (c.out_mode == KMPC_OUT_C) ? i : c.out_row;
+      const int row = (sh.out_mode == KMPC_OUT_C) ? i : c.out_row;
       ws.Cy[e] = (j < nz) ? C[row * nz + j] : 0.0;
     }
   }
   KMPC_LANE_LOOP(e, N) {
     double lo = c.lb, hi = c.ub;
-    if (c.du_aug && e == 0) {  // Tank_System.m:182-188: umin <= U0 + dU_1 <= umax
+    if (sh.du_aug && e == 0) {  // Tank_System.m:182-188: umin <= U0 + dU_1 <= umax
       lo = fmax(lo, c.u_lb - uprev);
       hi = fmin(hi, c.u_ub - uprev);
     }
@@ -61,11 +73,11 @@ KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, int64_t s, int64_t step, 
     ws.ub[e] = hi;
   }
   KMPC_SYNCWARP();
-  qp_build_warp(ws, nzq, ny, N, identity, c.q, c.rw, d.b.r + s * ny, 0, nullptr);
-  const int st = qp_solve_warp(ws, N, c.max_iter, c.tol);
-  if (KMPC_LANE0) {
+  qp_build_warp<G>(ws, nzq, ny, N, identity, c.q, c.rw, d.b.r + s * ny, 0, nullptr);
+  const int st = qp_solve_warp<G>(ws, N, c.max_iter, c.tol);
+  if (KMPC_LANE0 && valid) {
     const double move = ws.x[0];
-    const double u = c.du_aug ? uprev + move : move;
+    const double u = sh.du_aug ? uprev + move : move;
     const double* pp = (step < c.first_post_step ? d.b.params_pre : d.b.params_post) + s * 5;
     double p[5];
     for (int k = 0; k < 5; ++k) p[k] = pp[k];
@@ -89,9 +101,11 @@ KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, int64_t s, int64_t step, 
 // RLS with the sample (z, u) -> z_next; afterwards z <- z_next.  `first` = this is the restart
 // update (duffing.py:927-930, 943-946): state is initialised to P = p0 I, bar_Q = q0 I, K_A = 0,
 // bar_X = 0 instead of being read.
-KMPC_DEV void loop_rls_scenario(const LoopDev& d, int64_t s, int first, double* base) {
+template <int G>
+KMPC_DEV void loop_rls_scenario(const LoopDev& d, const int nz, int64_t s, bool valid, int first,
+                                double* base) {
   const kmpc_loop_config& c = d.c;
-  const int nz = c.nz, n = c.n, nv = nz + 1;
+  const int n = 2, nv = nz + 1;
   RlsWs ws = rls_ws_carve(base, nz, n);
   const bool upc = c.rls_flags & KMPC_RLS_UPDATE_C;
   if (first) {
@@ -116,7 +130,11 @@ KMPC_DEV void loop_rls_scenario(const LoopDev& d, int64_t s, int first, double* 
   KMPC_SYNCWARP();
   int flags = c.rls_flags;
   if (first && c.skip_first_barx) flags |= KMPC_RLS_SKIP_BARX;
-  rls_update_warp(ws, nz, n, c.lambda, flags, d.b.A + s * nz * nz, d.b.B + s * nz, d.b.C + s * n * nz);
+  rls_update_warp<G>(ws, nz, n, c.lambda, flags);
+  if (!valid) return;
+  KMPC_LANE_LOOP(e, nz * nz) d.b.A[s * nz * nz + e] = ws.oA[e];
+  KMPC_LANE_LOOP(e, nz) d.b.B[s * nz + e] = ws.oB[e];
+  if (upc) KMPC_LANE_LOOP(e, n * nz) d.b.C[s * n * nz + e] = ws.oC[e];
   KMPC_LANE_LOOP(e, nz * nv) d.b.KA[s * nz * nv + e] = ws.KA[e];
   KMPC_LANE_LOOP(e, nv * nv) d.b.P[s * nv * nv + e] = ws.P[e];
   if (upc) {

@@ -1,9 +1,12 @@
 // percase.cuh -- warp-per-scenario device functions: RLS update, condensed-QP build, exact
 // box-QP active-set solve, plant step, small SPD solves.
 //
-// Mapping: ONE WARP owns one scenario; all per-scenario matrices live in that warp's slice of
-// shared memory; work inside a phase is distributed over lanes with a lane-strided loop and
-// phases are separated by __syncwarp().  fp64 throughout (fp32 RLS diverges).
+// Mapping: a GROUP of G lanes (G = 32, 16 or 8, template parameter) owns one scenario, so a warp
+// carries 32/G scenarios; all per-scenario matrices live in that group's slice of shared memory;
+// work inside a phase is distributed over the group's lanes with a lane-strided loop and phases
+// are separated by __syncwarp() (all 32 lanes always execute the same phase sequence: groups
+// whose scenario index is past the end recompute the last scenario and skip the global writes).
+// fp64 throughout (fp32 RLS diverges).
 //
 // The same source compiles with a host compiler when KMPC_HOSTEMU is defined: a lane-strided
 // loop becomes a plain loop over all elements and the warp primitives become no-ops.  That build
@@ -25,22 +28,27 @@
 #define KMPC_LANE_LOOP(e, n) for (int e = 0; e < (n); ++e)
 #define KMPC_SYNCWARP() ((void)0)
 #define KMPC_LANE0 true
+#define KMPC_UNROLL
 #else
 #define KMPC_DEV __device__ __forceinline__
 #define KMPC_HD __host__ __device__
-#define KMPC_LANE_LOOP(e, n) for (int e = (int)(threadIdx.x & 31); e < (n); e += 32)
+// G (lanes per scenario) must be in scope as a compile-time constant
+#define KMPC_LANE_LOOP(e, n) for (int e = (int)(threadIdx.x & (G - 1)); e < (n); e += G)
 #define KMPC_SYNCWARP() __syncwarp()
-#define KMPC_LANE0 ((threadIdx.x & 31) == 0)
+#define KMPC_LANE0 ((threadIdx.x & (G - 1)) == 0)
+#define KMPC_UNROLL _Pragma("unroll")
 #endif
 
 namespace kmpc {
 
 // ---------------------------------------------------------------- warp reductions -----------
-// (value, index) argmin with lowest-index tie break; host build: identity.
-KMPC_DEV void warp_argmin(double& val, int& idx) {
+// Reductions over the G lanes of a group (xor offsets < G stay inside the aligned group);
+// host build: identity.  (value, index) argmin breaks ties towards the lowest index.
+template <int G>
+KMPC_DEV void group_argmin(double& val, int& idx) {
 #ifndef KMPC_HOSTEMU
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
+  for (int off = G / 2; off > 0; off >>= 1) {
     double ov = __shfl_xor_sync(0xffffffffu, val, off);
     int oi = __shfl_xor_sync(0xffffffffu, idx, off);
     if (ov < val || (ov == val && oi < idx)) {
@@ -50,19 +58,29 @@ KMPC_DEV void warp_argmin(double& val, int& idx) {
   }
 #endif
 }
-KMPC_DEV double warp_max(double v) {
+template <int G>
+KMPC_DEV double group_max(double v) {
 #ifndef KMPC_HOSTEMU
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+  for (int off = G / 2; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
 #endif
   return v;
 }
-KMPC_DEV int warp_or(int v) {
+template <int G>
+KMPC_DEV int group_or(int v) {
 #ifndef KMPC_HOSTEMU
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, off);
+  for (int off = G / 2; off > 0; off >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, off);
 #endif
   return v;
+}
+// true when any lane of the WARP has the predicate set (keeps the groups of a warp in lock step)
+KMPC_DEV bool warp_any(bool pred) {
+#ifndef KMPC_HOSTEMU
+  return __any_sync(0xffffffffu, pred);
+#else
+  return pred;
+#endif
 }
 
 // ---------------------------------------------------------------- plant ---------------------
@@ -112,10 +130,12 @@ struct RlsWs {
   double *KA, *P, *barX, *barQ;  // state: nz*nv, nv*nv, n*nz, nz*nz
   double *v, *y, *xc;            // sample: nv (= [z;u]), nz, n
   double *w, *rrow;              // P v, v'P (nv each; reused for bar_Q with nz)
+  double *oA, *oB, *oC;          // outputs staged here: nz*nz, nz, n*nz
 };
 KMPC_HD inline int rls_ws_doubles(int nz, int n) {
   int nv = nz + 1;
-  return nz * nv + nv * nv + n * nz + nz * nz + nv + nz + n + 2 * nv;
+  int t = nz * nv + nv * nv + n * nz + nz * nz + nv + nz + n + 2 * nv + nz * nz + nz + n * nz;
+  return (t + 1) & ~1;
 }
 KMPC_DEV RlsWs rls_ws_carve(double* base, int nz, int n) {
   int nv = nz + 1;
@@ -129,29 +149,35 @@ KMPC_DEV RlsWs rls_ws_carve(double* base, int nz, int n) {
   w.xc = w.y + nz;
   w.w = w.xc + n;
   w.rrow = w.w + nv;
+  w.oA = w.rrow + nv;
+  w.oB = w.oA + nz * nz;
+  w.oC = w.oB + nz;
   return w;
 }
 
-// State and sample already in ws.  Writes A (nz*nz), B (nz), C (n*nz) through the given pointers
-// (global or shared).  Formula order follows the reference (no symmetrisation of P).
-KMPC_DEV void rls_update_warp(const RlsWs& ws, int nz, int n, double lam, int flags, double* oA,
-                              double* oB, double* oC) {
+// State and sample already in ws.  Leaves A (nz*nz), B (nz), C (n*nz) in ws.oA / oB / oC.
+// Formula order follows the reference (no symmetrisation of P).
+template <int G>
+KMPC_DEV void rls_update_warp(const RlsWs& ws, int nz, int n, double lam, int flags) {
   const int nv = nz + 1;
+  double* oA = ws.oA;
+  double* oB = ws.oB;
+  double* oC = ws.oC;
   // w = P v (lanes 0..nv-1), rrow = v'P (next nv)
   KMPC_LANE_LOOP(o, 2 * nv) {
     double s = 0.0;
     if (o < nv) {
-      for (int j = 0; j < nv; ++j) s += ws.P[o * nv + j] * ws.v[j];
+      KMPC_UNROLL for (int j = 0; j < nv; ++j) s += ws.P[o * nv + j] * ws.v[j];
       ws.w[o] = s;
     } else {
       int j = o - nv;
-      for (int i = 0; i < nv; ++i) s += ws.v[i] * ws.P[i * nv + j];
+      KMPC_UNROLL for (int i = 0; i < nv; ++i) s += ws.v[i] * ws.P[i * nv + j];
       ws.rrow[j] = s;
     }
   }
   KMPC_SYNCWARP();
   double vPv = 0.0;  // (v'P) v, duffing.py:934
-  for (int j = 0; j < nv; ++j) vPv += ws.rrow[j] * ws.v[j];
+  KMPC_UNROLL for (int j = 0; j < nv; ++j) vPv += ws.rrow[j] * ws.v[j];
   const double denom = lam + vPv;
   KMPC_LANE_LOOP(e, nv * nv) {
     int i = e / nv, j = e - i * nv;
@@ -165,7 +191,7 @@ KMPC_DEV void rls_update_warp(const RlsWs& ws, int nz, int n, double lam, int fl
   KMPC_LANE_LOOP(e, nz * nv) {  // [A B] = K_A P
     int i = e / nv, j = e - i * nv;
     double s = 0.0;
-    for (int k = 0; k < nv; ++k) s += ws.KA[i * nv + k] * ws.P[k * nv + j];
+    KMPC_UNROLL for (int k = 0; k < nv; ++k) s += ws.KA[i * nv + k] * ws.P[k * nv + j];
     if (j < nz)
       oA[i * nz + j] = s;
     else
@@ -176,17 +202,17 @@ KMPC_DEV void rls_update_warp(const RlsWs& ws, int nz, int n, double lam, int fl
     KMPC_LANE_LOOP(o, 2 * nz) {  // w = bar_Q z, rrow = z' bar_Q  (z = v[0..nz))
       double s = 0.0;
       if (o < nz) {
-        for (int j = 0; j < nz; ++j) s += ws.barQ[o * nz + j] * ws.v[j];
+        KMPC_UNROLL for (int j = 0; j < nz; ++j) s += ws.barQ[o * nz + j] * ws.v[j];
         ws.w[o] = s;
       } else {
         int j = o - nz;
-        for (int i = 0; i < nz; ++i) s += ws.v[i] * ws.barQ[i * nz + j];
+        KMPC_UNROLL for (int i = 0; i < nz; ++i) s += ws.v[i] * ws.barQ[i * nz + j];
         ws.rrow[j] = s;
       }
     }
     KMPC_SYNCWARP();
     double zQz = 0.0;
-    for (int j = 0; j < nz; ++j) zQz += ws.rrow[j] * ws.v[j];
+    KMPC_UNROLL for (int j = 0; j < nz; ++j) zQz += ws.rrow[j] * ws.v[j];
     const double dq = 1.0 + zQz;
     KMPC_LANE_LOOP(e, nz * nz) {
       int i = e / nz, j = e - i * nz;
@@ -202,7 +228,7 @@ KMPC_DEV void rls_update_warp(const RlsWs& ws, int nz, int n, double lam, int fl
     KMPC_LANE_LOOP(e, n * nz) {  // C = bar_X bar_Q
       int i = e / nz, j = e - i * nz;
       double s = 0.0;
-      for (int k = 0; k < nz; ++k) s += ws.barX[i * nz + k] * ws.barQ[k * nz + j];
+      KMPC_UNROLL for (int k = 0; k < nz; ++k) s += ws.barX[i * nz + k] * ws.barQ[k * nz + j];
       oC[e] = s;
     }
   }
@@ -260,27 +286,26 @@ KMPC_DEV QpWs qp_ws_carve(double* base, int nzq, int ny, int N, bool identity) {
 // Build H (packed) and f from the model in ws (A, B, Cy, z0) and the reference r.
 //   r_stride = 0: r is (ny) constant over the horizon; r_stride = ny: r is (N, ny).
 //   PN: optional terminal weight (ny*ny, row-major) replacing the last q*I block (nullable).
+template <int G>
 KMPC_DEV void qp_build_warp(const QpWs& ws, int nzq, int ny, int N, bool identity, double q,
                             double rw, const double* r, int r_stride, const double* PN) {
   // ---- Krylov chains: VZ[t] = A VZ[t-1] (VZ[-1] = z0), VB[t+1] = A VB[t] (VB[0] = B);
-  //      lanes 0-15 advance the z chain, lanes 16-31 the B chain (nzq <= 16)
+  //      outputs 0..nzq-1 advance the z chain, nzq..2nzq-1 the B chain, in the same phase
   KMPC_LANE_LOOP(i, nzq) ws.VB[i] = ws.B[i];
   KMPC_SYNCWARP();
   for (int t = 0; t < N; ++t) {
-    KMPC_LANE_LOOP(o, 32) {
-      const int half = o >> 4, i = o & 15;
-      if (i < nzq) {
-        if (half == 0) {
-          const double* src = (t == 0) ? ws.z0 : ws.VZ + (t - 1) * nzq;
-          double s = 0.0;
-          for (int j = 0; j < nzq; ++j) s += ws.A[i * nzq + j] * src[j];
-          ws.VZ[t * nzq + i] = s;
-        } else if (t + 1 < N) {
-          const double* src = ws.VB + t * nzq;
-          double s = 0.0;
-          for (int j = 0; j < nzq; ++j) s += ws.A[i * nzq + j] * src[j];
-          ws.VB[(t + 1) * nzq + i] = s;
-        }
+    KMPC_LANE_LOOP(o, 2 * nzq) {
+      const int half = o >= nzq, i = half ? o - nzq : o;
+      if (half == 0) {
+        const double* src = (t == 0) ? ws.z0 : ws.VZ + (t - 1) * nzq;
+        double s = 0.0;
+        KMPC_UNROLL for (int j = 0; j < nzq; ++j) s += ws.A[i * nzq + j] * src[j];
+        ws.VZ[t * nzq + i] = s;
+      } else if (t + 1 < N) {
+        const double* src = ws.VB + t * nzq;
+        double s = 0.0;
+        KMPC_UNROLL for (int j = 0; j < nzq; ++j) s += ws.A[i * nzq + j] * src[j];
+        ws.VB[(t + 1) * nzq + i] = s;
       }
     }
     KMPC_SYNCWARP();
@@ -297,7 +322,7 @@ KMPC_DEV void qp_build_warp(const QpWs& ws, int nzq, int ny, int N, bool identit
       int t = oo / ny, c = oo - t * ny;
       const double* src = (which == 0 ? ws.VB : ws.VZ) + t * nzq;
       double s = 0.0;
-      for (int j = 0; j < nzq; ++j) s += ws.Cy[c * nzq + j] * src[j];
+      KMPC_UNROLL for (int j = 0; j < nzq; ++j) s += ws.Cy[c * nzq + j] * src[j];
       if (which == 0)
         ws.g[oo] = s;
       else
@@ -310,7 +335,7 @@ KMPC_DEV void qp_build_warp(const QpWs& ws, int nzq, int ny, int N, bool identit
     double run = 0.0;
     for (int t = 0; t + d < N; ++t) {
       double s = 0.0;
-      for (int c = 0; c < ny; ++c) s += ws.g[(t + d) * ny + c] * ws.g[t * ny + c];
+      KMPC_UNROLL for (int c = 0; c < ny; ++c) s += ws.g[(t + d) * ny + c] * ws.g[t * ny + c];
       run += q * s;
       int a = N - 1 - t;
       ws.H[tri(a, a - d)] = run + (d == 0 ? rw : 0.0);
@@ -320,7 +345,7 @@ KMPC_DEV void qp_build_warp(const QpWs& ws, int nzq, int ny, int N, bool identit
   KMPC_LANE_LOOP(a, N) {
     double s = 0.0;
     for (int k = a; k < N; ++k)
-      for (int c = 0; c < ny; ++c) s += ws.g[(k - a) * ny + c] * ws.e[k * ny + c];
+      KMPC_UNROLL for (int c = 0; c < ny; ++c) s += ws.g[(k - a) * ny + c] * ws.e[k * ny + c];
     ws.f[a] = 2.0 * q * s;
   }
   KMPC_SYNCWARP();
@@ -352,6 +377,7 @@ KMPC_DEV void qp_build_warp(const QpWs& ws, int nzq, int ny, int N, bool identit
 
 // Cholesky of the free block of 2H into ws.L (masked rows/cols become identity rows).
 // Returns KMPC_STATUS_PIVOT if a pivot was not positive.
+template <int G>
 KMPC_DEV int qp_chol_masked(const QpWs& ws, int N) {
   int status = 0;
   for (int j = 0; j < N; ++j) {
@@ -389,6 +415,7 @@ KMPC_DEV int qp_chol_masked(const QpWs& ws, int N) {
 }
 
 // Solve (L L') p = rhs in place in ws.p (rhs must be zero on masked entries).
+template <int G>
 KMPC_DEV void qp_chol_solve(const QpWs& ws, int N) {
   for (int j = 0; j < N; ++j) {  // forward, column oriented
     const double yj = ws.p[j] * ws.invd[j];
@@ -416,6 +443,7 @@ KMPC_DEV void qp_chol_solve(const QpWs& ws, int N) {
 }
 
 // grad = 2 H x + f
+template <int G>
 KMPC_DEV void qp_gradient(const QpWs& ws, int N) {
   KMPC_LANE_LOOP(i, N) {
     double s = 0.0;
@@ -427,6 +455,9 @@ KMPC_DEV void qp_gradient(const QpWs& ws, int N) {
 
 // Exact primal active-set solve of  min x'Hx + f'x,  lb <= x <= ub  (oracle/mpc.py
 // solve_box_qp_exact is the same algorithm).  Result in ws.x; returns status bits.
+// The groups of a warp iterate in lock step: a group that has converged keeps executing the
+// phases (its x and W are frozen) until every group of the warp is done.
+template <int G>
 KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol) {
   int status = 0;
   KMPC_LANE_LOOP(i, N) {
@@ -434,8 +465,8 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol) {
     ws.p[i] = -ws.f[i];
   }
   KMPC_SYNCWARP();
-  status |= qp_chol_masked(ws, N);
-  qp_chol_solve(ws, N);
+  status |= qp_chol_masked<G>(ws, N);
+  qp_chol_solve<G>(ws, N);
   int any = 0;
   double fmaxabs = 0.0;
   KMPC_LANE_LOOP(i, N) {
@@ -453,36 +484,38 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol) {
     any |= (w != 0);
     fmaxabs = fmax(fmaxabs, fabs(ws.f[i]));
   }
-  any = warp_or(any);
-  fmaxabs = warp_max(fmaxabs);
+  any = group_or<G>(any);
+  fmaxabs = group_max<G>(fmaxabs);
   KMPC_SYNCWARP();
-  if (any) {
-    const double mtol = tol * fmax(1.0, fmaxabs);
-    bool done = false;
-    for (int it = 0; it < max_iter && !done; ++it) {
-      qp_gradient(ws, N);
-      KMPC_LANE_LOOP(i, N) ws.p[i] = (ws.W[i] == 0) ? -ws.grad[i] : 0.0;
-      KMPC_SYNCWARP();
-      status |= qp_chol_masked(ws, N);
-      qp_chol_solve(ws, N);
-      // ratio test
-      double alpha = 1.0;
-      int block = 0x7fffffff;
-      KMPC_LANE_LOOP(i, N) {
-        if (ws.W[i] == 0) {
-          double pi = ws.p[i], xi = ws.x[i], a = 2.0;
-          if (pi > 0.0 && xi + pi > ws.ub[i])
-            a = (ws.ub[i] - xi) / pi;
-          else if (pi < 0.0 && xi + pi < ws.lb[i])
-            a = (ws.lb[i] - xi) / pi;
-          if (a < alpha) {  // strict: lowest index wins ties within a lane's ascending sweep
-            alpha = a;
-            block = i;
-          }
+  const double mtol = tol * fmax(1.0, fmaxabs);
+  bool done = !any;
+  if (warp_any(!done)) qp_gradient<G>(ws, N);  // grad at the clipped start; refreshed after each step
+  for (int it = 0; it < max_iter; ++it) {
+    if (!warp_any(!done)) break;
+    KMPC_LANE_LOOP(i, N) ws.p[i] = (ws.W[i] == 0) ? -ws.grad[i] : 0.0;
+    KMPC_SYNCWARP();
+    const int cst = qp_chol_masked<G>(ws, N);
+    if (!done) status |= cst;
+    qp_chol_solve<G>(ws, N);
+    // ratio test
+    double alpha = 1.0;
+    int block = 0x7fffffff;
+    KMPC_LANE_LOOP(i, N) {
+      if (ws.W[i] == 0) {
+        double pi = ws.p[i], xi = ws.x[i], a = 2.0;
+        if (pi > 0.0 && xi + pi > ws.ub[i])
+          a = (ws.ub[i] - xi) / pi;
+        else if (pi < 0.0 && xi + pi < ws.lb[i])
+          a = (ws.lb[i] - xi) / pi;
+        if (a < alpha) {  // strict: lowest index wins ties within a lane's ascending sweep
+          alpha = a;
+          block = i;
         }
       }
-      warp_argmin(alpha, block);
-      const bool blocked = block != 0x7fffffff;
+    }
+    group_argmin<G>(alpha, block);
+    const bool blocked = block != 0x7fffffff;
+    if (!done) {
       KMPC_LANE_LOOP(i, N) {
         double xi = ws.x[i] + alpha * ws.p[i];
         if (blocked && i == block) {
@@ -492,35 +525,37 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol) {
         }
         ws.x[i] = xi;
       }
-      KMPC_SYNCWARP();
-      if (blocked) continue;
-      // full step taken: multipliers of the bound variables
-      qp_gradient(ws, N);
-      double worst = INFINITY;
-      int widx = 0x7fffffff;
-      KMPC_LANE_LOOP(i, N) {
-        const int w = ws.W[i];
-        if (w != 0) {
-          const double lam = w < 0 ? ws.grad[i] : -ws.grad[i];
-          if (lam < worst) {
-            worst = lam;
-            widx = i;
-          }
+    }
+    KMPC_SYNCWARP();
+    // after a full step: multipliers of the bound variables (computed by every group to stay in
+    // lock step; only used by groups that took an unblocked step)
+    qp_gradient<G>(ws, N);
+    double worst = INFINITY;
+    int widx = 0x7fffffff;
+    KMPC_LANE_LOOP(i, N) {
+      const int w = ws.W[i];
+      if (w != 0) {
+        const double lam = w < 0 ? ws.grad[i] : -ws.grad[i];
+        if (lam < worst) {
+          worst = lam;
+          widx = i;
         }
       }
-      warp_argmin(worst, widx);
+    }
+    group_argmin<G>(worst, widx);
+    if (!done && !blocked) {
       if (widx == 0x7fffffff || worst >= -mtol) {
         done = true;
-      } else {
-        if (KMPC_LANE0) ws.W[widx] = 0;
-        KMPC_SYNCWARP();
+      } else if (KMPC_LANE0) {
+        ws.W[widx] = 0;
       }
     }
-    if (!done) status |= KMPC_STATUS_MAXITER;
+    KMPC_SYNCWARP();
   }
+  if (!done) status |= KMPC_STATUS_MAXITER;
   int bad = 0;
   KMPC_LANE_LOOP(i, N) bad |= !isfinite(ws.x[i]);
-  if (warp_or(bad)) status |= KMPC_STATUS_NONFINITE;
+  if (group_or<G>(bad)) status |= KMPC_STATUS_NONFINITE;
   return status;
 }
 
@@ -528,17 +563,18 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol) {
 // X = Bm * inv(G) for SPD G (n x n, row-major, destroyed) and Bm (rows x n): Cholesky of G then
 // two triangular solves per row.  Used by the EDMD solve (K = Aq G^-1).  Work arrays in smem or
 // global; single warp.
-KMPC_DEV int spd_right_solve_warp(double* G, int n, double* Bm, int rows) {
+template <int G>
+KMPC_DEV int spd_right_solve_warp(double* Gm, int n, double* Bm, int rows) {
   int status = 0;
   for (int j = 0; j < n; ++j) {  // in-place lower Cholesky, left-looking
     KMPC_LANE_LOOP(ii, n - j) {
       int i = j + ii;
-      double s = G[i * n + j];
-      for (int k = 0; k < j; ++k) s -= G[i * n + k] * G[j * n + k];
-      G[i * n + j] = s;
+      double s = Gm[i * n + j];
+      for (int k = 0; k < j; ++k) s -= Gm[i * n + k] * Gm[j * n + k];
+      Gm[i * n + j] = s;
     }
     KMPC_SYNCWARP();
-    double d = G[j * n + j];
+    double d = Gm[j * n + j];
     if (!(d > 0.0)) {
       status |= KMPC_STATUS_PIVOT;
       d = 1e-300;
@@ -547,7 +583,7 @@ KMPC_DEV int spd_right_solve_warp(double* G, int n, double* Bm, int rows) {
     KMPC_SYNCWARP();
     KMPC_LANE_LOOP(ii, n - j) {
       int i = j + ii;
-      G[i * n + j] = (ii == 0) ? piv : G[i * n + j] / piv;
+      Gm[i * n + j] = (ii == 0) ? piv : Gm[i * n + j] / piv;
     }
     KMPC_SYNCWARP();
   }
@@ -556,13 +592,13 @@ KMPC_DEV int spd_right_solve_warp(double* G, int n, double* Bm, int rows) {
     double* b = Bm + rr * n;
     for (int i = 0; i < n; ++i) {
       double s = b[i];
-      for (int k = 0; k < i; ++k) s -= G[i * n + k] * b[k];
-      b[i] = s / G[i * n + i];
+      for (int k = 0; k < i; ++k) s -= Gm[i * n + k] * b[k];
+      b[i] = s / Gm[i * n + i];
     }
     for (int i = n - 1; i >= 0; --i) {
       double s = b[i];
-      for (int k = i + 1; k < n; ++k) s -= G[k * n + i] * b[k];
-      b[i] = s / G[i * n + i];
+      for (int k = i + 1; k < n; ++k) s -= Gm[k * n + i] * b[k];
+      b[i] = s / Gm[i * n + i];
     }
   }
   KMPC_SYNCWARP();

@@ -15,7 +15,7 @@ rls_update_kernel(double* __restrict__ KA, double* __restrict__ P, double* __res
                   double* __restrict__ C, int64_t S, int nz, int n, double lam, int flags) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (s >= S) return;
   const int nv = nz + 1;
   RlsWs ws = rls_ws_carve(smem + (size_t)warp * rls_ws_doubles(nz, n), nz, n);
@@ -32,7 +32,11 @@ rls_update_kernel(double* __restrict__ KA, double* __restrict__ P, double* __res
   }
   if (lane == 0) ws.v[nz] = u[s];
   __syncwarp();
-  rls_update_warp(ws, nz, n, lam, flags, A + s * nz * nz, B + s * nz, C + s * n * nz);
+  rls_update_warp<32>(ws, nz, n, lam, flags);
+  for (int e = lane; e < nz * nz; e += 32) A[s * nz * nz + e] = ws.oA[e];
+  for (int e = lane; e < nz; e += 32) B[s * nz + e] = ws.oB[e];
+  if (flags & KMPC_RLS_UPDATE_C)
+    for (int e = lane; e < n * nz; e += 32) C[s * n * nz + e] = ws.oC[e];
   for (int e = lane; e < nz * nv; e += 32) KA[s * nz * nv + e] = ws.KA[e];
   for (int e = lane; e < nv * nv; e += 32) P[s * nv * nv + e] = ws.P[e];
   if (flags & KMPC_RLS_UPDATE_C) {
@@ -52,7 +56,7 @@ qp_first_move_kernel(const double* __restrict__ A, const double* __restrict__ B,
                      int max_iter, double tol) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t s = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (s >= S) return;
   const bool identity = flags & KMPC_QP_CY_IDENTITY;
   const bool shared_model = flags & KMPC_QP_SHARED_MODEL;
@@ -73,8 +77,8 @@ qp_first_move_kernel(const double* __restrict__ A, const double* __restrict__ B,
   __syncwarp();
   const double* rs = r_full ? r + s * N * ny : r + s * ny;
   const double* pn = PN ? PN + sm * ny * ny : nullptr;
-  qp_build_warp(ws, nz, ny, N, identity, q, rw, rs, r_full ? ny : 0, pn);
-  const int st = qp_solve_warp(ws, N, max_iter, tol);
+  qp_build_warp<32>(ws, nz, ny, N, identity, q, rw, rs, r_full ? ny : 0, pn);
+  const int st = qp_solve_warp<32>(ws, N, max_iter, tol);
   if (lane == 0) {
     u0[s] = ws.x[0];
     if (status) status[s] = st;
@@ -119,14 +123,16 @@ extern "C" {
 int kmpc_rls_update(double* KA, double* P, double* barX, double* barQ, const double* z,
                     const double* u, const double* y, const double* xc, double* A, double* B,
                     double* C, int64_t S, int nz, int n, double lambda, int flags, void* stream) {
+  if (nz < 1 || nz > KMPC_MAX_NZ || n < 1 || n > 4 || !(lambda > 0.0) || S < 0) return KMPC_ERR_ARG;
+  if (S == 0) return KMPC_OK;  // empty batch: nothing to validate (empty tensors have null data)
   if (!KA || !P || !z || !u || !y || !A || !B) return KMPC_ERR_ARG;
   if ((flags & KMPC_RLS_UPDATE_C) && (!barX || !barQ || !xc || !C)) return KMPC_ERR_ARG;
-  if (nz < 1 || nz > KMPC_MAX_NZ || n < 1 || n > 4 || !(lambda > 0.0) || S < 0) return KMPC_ERR_ARG;
-  if (S == 0) return KMPC_OK;
-  const int smem = kWarpsPerBlock * rls_ws_doubles(nz, n) * (int)sizeof(double);
+  const int wpb = warps_that_fit(rls_ws_doubles(nz, n));
+  if (wpb < 1) return KMPC_ERR_UNSUPPORTED;
+  const int smem = wpb * rls_ws_doubles(nz, n) * (int)sizeof(double);
   KMPC_CUDA(ensure_smem(rls_update_kernel, smem));
-  const unsigned grid = (unsigned)((S + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  rls_update_kernel<<<grid, kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
+  const unsigned grid = (unsigned)((S + wpb - 1) / wpb);
+  rls_update_kernel<<<grid, wpb * 32, smem, as_stream(stream)>>>(
       KA, P, barX, barQ, z, u, y, xc, A, B, C, S, nz, n, lambda, flags);
   KMPC_AFTER_LAUNCH();
   return KMPC_OK;
@@ -137,19 +143,21 @@ int kmpc_qp_first_move(const double* A, const double* B, const double* Cy, const
                        double q, double rw, int N, int ny, int nz, int64_t S, int flags,
                        double* u0, double* Ufull, int* status, int max_iter, double tol,
                        void* stream) {
-  if (!A || !B || !z0 || !r || !lb || !ub || !u0) return KMPC_ERR_ARG;
   const bool identity = flags & KMPC_QP_CY_IDENTITY;
-  if (!identity && !Cy) return KMPC_ERR_ARG;
   if (identity && ny != nz) return KMPC_ERR_ARG;
   if (nz < 1 || nz > KMPC_MAX_NZ || ny < 1 || ny > KMPC_MAX_NZ || N < 1 || N > KMPC_MAX_HORIZON || S < 0)
     return KMPC_ERR_ARG;
   if (S == 0) return KMPC_OK;
+  if (!A || !B || !z0 || !r || !lb || !ub || !u0) return KMPC_ERR_ARG;
+  if (!identity && !Cy) return KMPC_ERR_ARG;
   if (max_iter <= 0) max_iter = 10 * N + 20;
   if (!(tol > 0.0)) tol = 1e-10;
-  const int smem = kWarpsPerBlock * qp_ws_doubles(nz, ny, N, identity) * (int)sizeof(double);
+  const int wpb = warps_that_fit(qp_ws_doubles(nz, ny, N, identity));
+  if (wpb < 1) return KMPC_ERR_UNSUPPORTED;
+  const int smem = wpb * qp_ws_doubles(nz, ny, N, identity) * (int)sizeof(double);
   KMPC_CUDA(ensure_smem(qp_first_move_kernel, smem));
-  const unsigned grid = (unsigned)((S + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  qp_first_move_kernel<<<grid, kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
+  const unsigned grid = (unsigned)((S + wpb - 1) / wpb);
+  qp_first_move_kernel<<<grid, wpb * 32, smem, as_stream(stream)>>>(
       A, B, Cy, z0, r, lb, ub, PN, q, rw, N, ny, nz, S, flags, u0, Ufull, status, max_iter, tol);
   KMPC_AFTER_LAUNCH();
   return KMPC_OK;
@@ -157,9 +165,10 @@ int kmpc_qp_first_move(const double* A, const double* B, const double* Cy, const
 
 int kmpc_plant_step(const double* x, const double* u, const double* params, double* xnext,
                     int64_t S, int kind, int rk4_variant, double h, void* stream) {
-  if (!x || !u || !params || !xnext || S < 0) return KMPC_ERR_ARG;
   if (kind != KMPC_PLANT_POLY2 && kind != KMPC_PLANT_TANK) return KMPC_ERR_ARG;
+  if (S < 0) return KMPC_ERR_ARG;
   if (S == 0) return KMPC_OK;
+  if (!x || !u || !params || !xnext) return KMPC_ERR_ARG;
   const unsigned grid = (unsigned)((S + 127) / 128);
   plant_step_kernel<<<grid, 128, 0, as_stream(stream)>>>(x, u, params, xnext, S, kind, rk4_variant, h);
   KMPC_AFTER_LAUNCH();
@@ -168,9 +177,10 @@ int kmpc_plant_step(const double* x, const double* u, const double* params, doub
 
 int kmpc_rbf_lift(const double* x, const double* cx, double* z, int64_t S, int n, int nz,
                   int variant, void* stream) {
-  if (!x || !cx || !z || S < 0 || n < 1 || n > 4 || nz < 1) return KMPC_ERR_ARG;
+  if (S < 0 || n < 1 || n > 4 || nz < 1) return KMPC_ERR_ARG;
   if (variant != KMPC_RBF_PYTHON && variant != KMPC_RBF_MATLAB) return KMPC_ERR_ARG;
   if (S == 0) return KMPC_OK;
+  if (!x || !cx || !z) return KMPC_ERR_ARG;
   const int64_t total = S * nz;
   const unsigned grid = (unsigned)((total + 255) / 256);
   rbf_lift_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, cx, z, S, n, nz, variant);

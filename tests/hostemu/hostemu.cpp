@@ -32,7 +32,10 @@ int emu_rls_update(double* KA, double* P, double* barX, double* barQ, const doub
     memcpy(ws.v, z + s * nz, sizeof(double) * nz);
     memcpy(ws.y, y + s * nz, sizeof(double) * nz);
     ws.v[nz] = u[s];
-    rls_update_warp(ws, nz, n, lambda, flags, A + s * nz * nz, B + s * nz, C ? C + s * n * nz : nullptr);
+    rls_update_warp<32>(ws, nz, n, lambda, flags);
+    memcpy(A + s * nz * nz, ws.oA, sizeof(double) * nz * nz);
+    memcpy(B + s * nz, ws.oB, sizeof(double) * nz);
+    if ((flags & KMPC_RLS_UPDATE_C) && C) memcpy(C + s * n * nz, ws.oC, sizeof(double) * n * nz);
     memcpy(KA + s * nz * nv, ws.KA, sizeof(double) * nz * nv);
     memcpy(P + s * nv * nv, ws.P, sizeof(double) * nv * nv);
     if (flags & KMPC_RLS_UPDATE_C) {
@@ -65,12 +68,12 @@ int emu_qp_first_move(const double* A, const double* B, const double* Cy, const 
     memcpy(ws.ub, ub + s * N, sizeof(double) * N);
     const double* rs = r_full ? r + s * N * ny : r + s * ny;
     const double* pn = PN ? PN + sm * ny * ny : nullptr;
-    qp_build_warp(ws, nz, ny, N, identity, q, rw, rs, r_full ? ny : 0, pn);
+    qp_build_warp<32>(ws, nz, ny, N, identity, q, rw, rs, r_full ? ny : 0, pn);
     if (Hout)
       for (int i = 0; i < N; ++i)
         for (int j = 0; j < N; ++j) Hout[(s * N + i) * N + j] = ws.H[i >= j ? tri(i, j) : tri(j, i)];
     if (fout) memcpy(fout + s * N, ws.f, sizeof(double) * N);
-    const int st = qp_solve_warp(ws, N, max_iter, tol);
+    const int st = qp_solve_warp<32>(ws, N, max_iter, tol);
     u0[s] = ws.x[0];
     if (status) status[s] = st;
     if (Ufull) memcpy(Ufull + s * N, ws.x, sizeof(double) * N);
@@ -94,7 +97,7 @@ int emu_rbf_lift(const double* x, const double* cx, double* z, int64_t S, int n,
 
 // X = Bm inv(G); G (n x n) is destroyed
 int emu_spd_right_solve(double* G, int n, double* Bm, int rows) {
-  return spd_right_solve_warp(G, n, Bm, rows);
+  return spd_right_solve_warp<32>(G, n, Bm, rows);
 }
 
 // ---- fused closed loop, same schedule as kmpc_closed_loop_steps (closed_loop.cu): per step
@@ -156,12 +159,12 @@ int emu_closed_loop(const kmpc_loop_config* cfg, const kmpc_loop_buffers* buf, i
   int64_t step = start_step;
   for (int t = 0; t < T; ++t, ++step) {
     const int64_t slot = step < d.b.log_capacity ? step : -1;
-    for (int64_t s = 0; s < c.S; ++s) loop_qp_plant_scenario(d, s, step, slot, qws.data());
+    for (int64_t s = 0; s < c.S; ++s) loop_qp_plant_scenario<32>(d, loop_shape(c), s, true, step, slot, qws.data());
     double* zdst = c.update ? d.z_next : d.b.z;
     for (int64_t s = 0; s < c.S; ++s)
       host_lift(c, d.b, n_layers, dims, W, bias, d.b.x + s * c.n, zdst + s * c.nz);
     if (c.update) {
-      for (int64_t s = 0; s < c.S; ++s) loop_rls_scenario(d, s, rls_started ? 0 : 1, rws.data());
+      for (int64_t s = 0; s < c.S; ++s) loop_rls_scenario<32>(d, c.nz, s, true, rls_started ? 0 : 1, rws.data());
       rls_started = 1;
     }
   }
