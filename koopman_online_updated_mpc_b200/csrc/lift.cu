@@ -9,10 +9,15 @@
 // padded ([in][out_pad], out_pad multiple of 4), packed layer after layer in one device buffer.
 // Each thread owns a 4 (scenarios) x 4 (outputs) register tile: 16 DFMA per 8 x 8-byte operands.
 //
-// encoder_smem_kernel (default): the whole packed weight set (171 KB for 2-100-100-100-8) is
+// encoder_mma_kernel (default): the whole packed weight set (182 KB for 2-100-100-100-8) is
 // brought into shared memory ONCE per CTA by the TMA engine (cp.async.bulk, one mbarrier per
-// layer so layer 1 starts while layers 2.. are still in flight); CTAs are persistent over tiles.
-// encoder_kernel (fallback for nets that do not fit 227 KB): weights read from global/L2.
+// layer so layer 1 starts while layers 2.. are still in flight); CTAs are persistent over tiles;
+// the layer GEMMs run on the fp64 tensor path (mma.sync m8n8k4 f64 -- tcgen05 has no f64 kind, and
+// DMMA measures the same 37 TFLOP/s as DFMA on B200, but needs 8x fewer shared-memory wavefronts
+// per MAC, which is what bounded the CUDA-core version).  Row strides of the activation (36) and
+// weight (== 4 mod 16) arrays make every fragment load bank-conflict free.
+// encoder_kernel (fallback for nets that do not fit 227 KB): CUDA-core 4x4 register tiles,
+// weights read from global/L2.
 #include <vector>
 
 #include "common.cuh"
@@ -35,6 +40,8 @@ struct EncParams {
   int wlen[KMPC_MAX_LAYERS];       // doubles of layer l's W + bias block
   int total_w;                     // doubles in `packed`
   int actw;                        // activation buffer width (max padded layer width)
+  int wstride[KMPC_MAX_LAYERS];    // row stride (doubles) of layer l's W^T block, == 4 (mod 16)
+  int inpad[KMPC_MAX_LAYERS];      // rows of layer l's W^T block (in rounded up to 4, zero rows)
 };
 
 // ---- TMA bulk-copy / mbarrier helpers (PTX; SASS: UBLKCP, SYNCS) --------------------------------
@@ -151,14 +158,26 @@ __device__ __forceinline__ void enc_store_tile(const double (&acc)[4][4], bool l
   }
 }
 
-// Persistent CTAs, weights resident in shared memory (loaded once by TMA bulk copies).
-__global__ void __launch_bounds__(kEncThreads, 1)
-encoder_smem_kernel(EncParams p, const double* __restrict__ x, double* __restrict__ z, int64_t S,
-                    int lift_mode, int out_dim, int64_t num_tiles) {
+constexpr int kMmaWarps = 8;
+constexpr int kMmaThreads = kMmaWarps * 32;
+constexpr int kActStride = 36;  // doubles per activation row k: 32 scenarios + 4 pad (== 4 mod 16)
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Persistent CTAs, weights resident in shared memory (loaded once by TMA bulk copies), layer GEMMs
+// on the fp64 tensor path.  Warp w owns rows 16*(w&1)..+15 (two m-tiles) and the n-tiles
+// {w>>1, (w>>1)+4, ...} of every layer; activations live in ONE k-major buffer that is rewritten
+// in place between two barriers.
+__global__ void __launch_bounds__(kMmaThreads, 1)
+encoder_mma_kernel(EncParams p, const double* __restrict__ x, double* __restrict__ z, int64_t S,
+                   int lift_mode, int out_dim, int64_t num_tiles) {
   extern __shared__ __align__(16) double smem[];
-  double* act_in = smem;
-  double* act_out = smem + p.actw * kTileS;
-  double* wsm = smem + 2 * p.actw * kTileS;
+  double* act = smem;
+  double* wsm = smem + p.actw * kActStride;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + p.total_w);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -178,40 +197,99 @@ encoder_smem_kernel(EncParams p, const double* __restrict__ x, double* __restric
     }
   }
   const int n = p.dims[0];
-  const int rg = lane & 7, cgl = lane >> 3;
   const int off = (lift_mode == KMPC_LIFT_STACK) ? n : 0;
+  const int gid = lane >> 2, tig = lane & 3;   // mma fragment coordinates
+  const int mrow = 16 * (warp & 1);            // first row of this warp's two m-tiles
+  const int ng = warp >> 1;                    // n-tile group
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTileS;
-    for (int e = tid; e < kTileS * n; e += kEncThreads) {
-      const int r = e / n, k = e - r * n;
-      const double v = (row0 + r < S) ? x[(row0 + r) * n + k] : 0.0;
-      act_in[k * kTileS + r] = v;
-      if (lift_mode == KMPC_LIFT_STACK && row0 + r < S) z[(row0 + r) * out_dim + k] = v;
+    // layer-0 input, k-major, rows [n, inpad) zero
+    for (int e = tid; e < kTileS * p.inpad[0]; e += kMmaThreads) {
+      const int k = e / kTileS, r = e - k * kTileS;
+      double v = 0.0;
+      if (k < n && row0 + r < S) {
+        v = x[(row0 + r) * n + k];
+        if (lift_mode == KMPC_LIFT_STACK) z[(row0 + r) * out_dim + k] = v;
+      }
+      act[k * kActStride + r] = v;
     }
     __syncthreads();
     for (int l = 0; l < p.n_layers; ++l) {
-      const int in = p.dims[l], outp = p.pad[l + 1], out = p.dims[l + 1];
-      const int ncg = outp >> 2;
+      const int kin = p.inpad[l], out = p.dims[l + 1], ws = p.wstride[l];
+      const int nt = (out + 7) >> 3;
       const bool last = (l == p.n_layers - 1);
       mbar_wait(&bars[l], 0);  // layer l's weights have landed (returns at once after the first tile)
       const double* wt = wsm + p.woff[l];
-      const double* bias = wt + in * outp;
-      for (int cg0 = 0; cg0 < ncg; cg0 += kEncWarps * 4) {
-        const int cg = cg0 + warp * 4 + cgl;
-        if (cg < ncg) {
-          double acc[4][4];
-          enc_layer_tile<false>(act_in + 4 * rg, wt + 4 * cg, bias + 4 * cg, in, outp, acc);
-          enc_store_tile(acc, last, act_out, cg, rg, z, row0, S, out, out_dim, off, lift_mode, p.z0);
+      const double* bias = wt + kin * ws;
+      double c[2][4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n0 = (ng + 4 * j) * 8;
+        const double b0 = (ng + 4 * j < nt) ? bias[n0 + 2 * tig] : 0.0;
+        const double b1 = (ng + 4 * j < nt) ? bias[n0 + 2 * tig + 1] : 0.0;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          c[m][j][0] = b0;
+          c[m][j][1] = b1;
+        }
+      }
+      const double* ap = act + tig * kActStride + mrow + gid;
+      const double* bp = wt + tig * ws + ng * 8 + gid;
+#pragma unroll 2
+      for (int k0 = 0; k0 < kin; k0 += 4) {
+        const double a0 = ap[k0 * kActStride];
+        const double a1 = ap[k0 * kActStride + 8];
+        double b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = (ng + 4 * j < nt) ? bp[k0 * ws + 32 * j] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (ng + 4 * j < nt) {  // warp-uniform
+            dmma_m8n8k4(c[0][j][0], c[0][j][1], a0, b[j]);
+            dmma_m8n8k4(c[1][j][0], c[1][j][1], a1, b[j]);
+          }
+        }
+      }
+      __syncthreads();  // every warp has finished reading the activations of this layer
+      if (!last) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (ng + 4 * j < nt) {
+            const int col = (ng + 4 * j) * 8 + 2 * tig;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              const int r = mrow + 8 * m + gid;
+              act[col * kActStride + r] = fmax(c[m][j][0], 0.0);
+              act[(col + 1) * kActStride + r] = fmax(c[m][j][1], 0.0);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (ng + 4 * j < nt) {
+            const int col = (ng + 4 * j) * 8 + 2 * tig;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              const int64_t row = row0 + mrow + 8 * m + gid;
+              if (row < S) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  if (col + q < out) {
+                    double v = c[m][j][q];
+                    if (lift_mode != KMPC_LIFT_RAW) v -= p.z0[col + q];
+                    z[row * out_dim + off + col + q] = v;
+                  }
+                }
+              }
+            }
+          }
         }
       }
       __syncthreads();
-      double* t = act_in;
-      act_in = act_out;
-      act_out = t;
     }
   }
 }
-
 
 __global__ void __launch_bounds__(kEncThreads)
 encoder_kernel(EncParams p, const double* __restrict__ x, double* __restrict__ z, int64_t S,
@@ -271,9 +349,9 @@ static int launch_encoder(const kmpc_encoder* enc, const double* x, double* z, i
   if (tiles > 0x7fffffff) return KMPC_ERR_ARG;
   const int out_dim = kmpc_encoder_out_dim(enc, lift_mode);
   if (enc->smem_bytes > 0) {
-    KMPC_CUDA(ensure_smem(encoder_smem_kernel, enc->smem_bytes));
+    KMPC_CUDA(ensure_smem(encoder_mma_kernel, enc->smem_bytes));
     const unsigned grid = (unsigned)(tiles < enc->num_sms ? tiles : enc->num_sms);
-    encoder_smem_kernel<<<grid, kEncThreads, enc->smem_bytes, st>>>(enc->p, x, z, S, lift_mode, out_dim, tiles);
+    encoder_mma_kernel<<<grid, kMmaThreads, enc->smem_bytes, st>>>(enc->p, x, z, S, lift_mode, out_dim, tiles);
   } else {
     const int smem = 2 * KMPC_MAX_WIDTH * kTileS * (int)sizeof(double);
     KMPC_CUDA(ensure_smem(encoder_kernel, smem));
@@ -302,42 +380,63 @@ int kmpc_encoder_create(kmpc_encoder** out, const double* const* W, const double
     kmpc_encoder_destroy(enc);
     return code;
   };
-  // pack [W1t | b1 | W2t | b2 | ...]: transposed, output-padded, exactly the smem layout
-  std::vector<double> packed;
+  // (a) tensor-path layout, exactly what encoder_mma_kernel keeps in shared memory:
+  //     per layer W^T as [inpad][wstride] (zero rows/cols beyond in/out; wstride == 4 mod 16 so the
+  //     4 k-rows of a B fragment hit disjoint banks) followed by the bias padded to 8.
+  // (b) fallback layout for encoder_kernel: W^T as [in][pad4(out)], bias pad4(out).
+  std::vector<double> packed, flat;
   int actw = 4;
+  std::vector<size_t> foff(n_layers);
   for (int l = 0; l < n_layers; ++l) {
     const int in = dims[l], o = dims[l + 1], op = enc->p.pad[l + 1];
+    const int inpad = (in + 3) & ~3, o8 = (o + 7) & ~7;
+    int wsd = (o + 3) & ~3;
+    while ((wsd & 15) != 4) wsd += 4;
+    enc->p.inpad[l] = inpad;
+    enc->p.wstride[l] = wsd;
     enc->p.woff[l] = (int)packed.size();
-    enc->p.wlen[l] = in * op + op;
-    packed.resize(packed.size() + (size_t)in * op + op, 0.0);
+    enc->p.wlen[l] = inpad * wsd + o8;
+    packed.resize(packed.size() + (size_t)inpad * wsd + o8, 0.0);
     double* wt = packed.data() + enc->p.woff[l];
-    double* bp = wt + (size_t)in * op;
+    double* bp = wt + (size_t)inpad * wsd;
+    foff[l] = flat.size();
+    flat.resize(flat.size() + (size_t)in * op + op, 0.0);
+    double* fw = flat.data() + foff[l];
+    double* fb = fw + (size_t)in * op;
     for (int i = 0; i < o; ++i) {
       bp[i] = b[l][i];
-      for (int k = 0; k < in; ++k) wt[(size_t)k * op + i] = W[l][(size_t)i * in + k];
+      fb[i] = b[l][i];
+      for (int k = 0; k < in; ++k) {
+        wt[(size_t)k * wsd + i] = W[l][(size_t)i * in + k];
+        fw[(size_t)k * op + i] = W[l][(size_t)i * in + k];
+      }
     }
-    if (enc->p.pad[l] > actw) actw = enc->p.pad[l];
-    if (l + 1 < n_layers && op > actw) actw = op;
+    if (inpad > actw) actw = inpad;
+    if (l + 1 < n_layers && ((o + 7) & ~7) > actw) actw = (o + 7) & ~7;
   }
+  packed.resize(packed.size() + 16, 0.0);  // slack: the last n-tile of a layer may read past its row
   enc->p.total_w = (int)packed.size();
   enc->p.actw = actw;
-  double* dpk = nullptr;
+  double *dpk = nullptr, *dfl = nullptr;
   if (cudaMalloc(&dpk, packed.size() * sizeof(double)) != cudaSuccess) return fail(KMPC_ERR_ALLOC);
   enc->owned.push_back(dpk);
+  if (cudaMalloc(&dfl, flat.size() * sizeof(double)) != cudaSuccess) return fail(KMPC_ERR_ALLOC);
+  enc->owned.push_back(dfl);
   // pageable-source async copies complete w.r.t. the host before returning
-  if (cudaMemcpyAsync(dpk, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess)
+  if (cudaMemcpyAsync(dpk, packed.data(), packed.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(dfl, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess)
     return fail(KMPC_ERR_CUDA);
   enc->p.packed = dpk;
   for (int l = 0; l < n_layers; ++l) {
-    enc->p.wt[l] = dpk + enc->p.woff[l];
-    enc->p.b[l] = dpk + enc->p.woff[l] + (size_t)dims[l] * enc->p.pad[l + 1];
+    enc->p.wt[l] = dfl + foff[l];
+    enc->p.b[l] = dfl + foff[l] + (size_t)dims[l] * enc->p.pad[l + 1];
   }
   {
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&enc->num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const size_t need = ((size_t)2 * actw * kTileS + packed.size()) * sizeof(double) + KMPC_MAX_LAYERS * 8;
+    const size_t need = ((size_t)actw * kActStride + packed.size()) * sizeof(double) + KMPC_MAX_LAYERS * 8;
     enc->smem_bytes = (need <= (size_t)max_smem) ? (int)need : 0;
   }
   // theta(0) for the OFFSET / STACK lift modes (Koopman_update.m:67)

@@ -23,6 +23,7 @@
 #include "../../include/kmpc.h"
 
 #ifdef KMPC_HOSTEMU
+inline double rsqrt(double v) { return 1.0 / sqrt(v); }
 #define KMPC_DEV inline
 #define KMPC_HD
 #define KMPC_LANE_LOOP(e, n) for (int e = 0; e < (n); ++e)
@@ -397,8 +398,8 @@ KMPC_DEV int qp_chol_masked(const QpWs& ws, int N) {
       status |= KMPC_STATUS_PIVOT;
       d = 1e-300;
     }
-    const double piv = sqrt(d);
-    const double inv = 1.0 / piv;
+    const double inv = rsqrt(d);  // one MUFU + Newton instead of sqrt followed by a division
+    const double piv = d * inv;
     KMPC_SYNCWARP();  // everyone has read L[j][j] before it is overwritten
     KMPC_LANE_LOOP(ii, N - j) {
       int i = j + ii;
@@ -453,10 +454,17 @@ KMPC_DEV void qp_gradient(const QpWs& ws, int N) {
   KMPC_SYNCWARP();
 }
 
-// Exact primal active-set solve of  min x'Hx + f'x,  lb <= x <= ub  (oracle/mpc.py
-// solve_box_qp_exact is the same algorithm).  Result in ws.x; returns status bits.
+// Exact solve of  min x'Hx + f'x,  lb <= x <= ub  (oracle/mpc.py solve_box_qp_exact is the same
+// algorithm).  Start: clipped unconstrained minimiser, clipped variables in the working set.
+// Iterations 0..kPdasIters-1 are primal-dual active-set sweeps (full Newton step on the free
+// face, then clip EVERY violated bound and release EVERY bound with a negative multiplier; stop
+// when nothing changes: KKT holds exactly); later iterations, reached only if the sweeps cycle,
+// are the monotone primal active-set method (ratio test; add the blocking bound or drop the most
+// negative multiplier), which always terminates.  Result in ws.x; returns status bits.
 // The groups of a warp iterate in lock step: a group that has converged keeps executing the
 // phases (its x and W are frozen) until every group of the warp is done.
+constexpr int kPdasIters = 8;
+
 template <int G>
 KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol) {
   int status = 0;
@@ -492,28 +500,30 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol) {
   if (warp_any(!done)) qp_gradient<G>(ws, N);  // grad at the clipped start; refreshed after each step
   for (int it = 0; it < max_iter; ++it) {
     if (!warp_any(!done)) break;
+    const bool pdas = it < kPdasIters;  // uniform over the warp
     KMPC_LANE_LOOP(i, N) ws.p[i] = (ws.W[i] == 0) ? -ws.grad[i] : 0.0;
     KMPC_SYNCWARP();
     const int cst = qp_chol_masked<G>(ws, N);
     if (!done) status |= cst;
     qp_chol_solve<G>(ws, N);
-    // ratio test
     double alpha = 1.0;
     int block = 0x7fffffff;
-    KMPC_LANE_LOOP(i, N) {
-      if (ws.W[i] == 0) {
-        double pi = ws.p[i], xi = ws.x[i], a = 2.0;
-        if (pi > 0.0 && xi + pi > ws.ub[i])
-          a = (ws.ub[i] - xi) / pi;
-        else if (pi < 0.0 && xi + pi < ws.lb[i])
-          a = (ws.lb[i] - xi) / pi;
-        if (a < alpha) {  // strict: lowest index wins ties within a lane's ascending sweep
-          alpha = a;
-          block = i;
+    if (!pdas) {  // ratio test
+      KMPC_LANE_LOOP(i, N) {
+        if (ws.W[i] == 0) {
+          double pi = ws.p[i], xi = ws.x[i], a = 2.0;
+          if (pi > 0.0 && xi + pi > ws.ub[i])
+            a = (ws.ub[i] - xi) / pi;
+          else if (pi < 0.0 && xi + pi < ws.lb[i])
+            a = (ws.lb[i] - xi) / pi;
+          if (a < alpha) {  // strict: lowest index wins ties within a lane's ascending sweep
+            alpha = a;
+            block = i;
+          }
         }
       }
+      group_argmin<G>(alpha, block);
     }
-    group_argmin<G>(alpha, block);
     const bool blocked = block != 0x7fffffff;
     if (!done) {
       KMPC_LANE_LOOP(i, N) {
@@ -527,30 +537,61 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol) {
       }
     }
     KMPC_SYNCWARP();
-    // after a full step: multipliers of the bound variables (computed by every group to stay in
-    // lock step; only used by groups that took an unblocked step)
-    qp_gradient<G>(ws, N);
-    double worst = INFINITY;
-    int widx = 0x7fffffff;
-    KMPC_LANE_LOOP(i, N) {
-      const int w = ws.W[i];
-      if (w != 0) {
-        const double lam = w < 0 ? ws.grad[i] : -ws.grad[i];
-        if (lam < worst) {
-          worst = lam;
-          widx = i;
+    qp_gradient<G>(ws, N);  // at the new point (PDAS: the unclipped face minimiser)
+    if (pdas) {
+      int changed = 0, clipped = 0;
+      if (!done) {
+        KMPC_LANE_LOOP(i, N) {
+          const int w = ws.W[i];
+          if (w != 0) {  // release every bound whose multiplier has the wrong sign
+            const double lam = w < 0 ? ws.grad[i] : -ws.grad[i];
+            if (lam < -mtol) {
+              ws.W[i] = 0;
+              changed = 1;
+            }
+          } else {       // clip every violated bound into the working set
+            const double xi = ws.x[i];
+            if (xi < ws.lb[i]) {
+              ws.x[i] = ws.lb[i];
+              ws.W[i] = -1;
+              clipped = 1;
+            } else if (xi > ws.ub[i]) {
+              ws.x[i] = ws.ub[i];
+              ws.W[i] = 1;
+              clipped = 1;
+            }
+          }
         }
       }
-    }
-    group_argmin<G>(worst, widx);
-    if (!done && !blocked) {
-      if (widx == 0x7fffffff || worst >= -mtol) {
-        done = true;
-      } else if (KMPC_LANE0) {
-        ws.W[widx] = 0;
+      clipped = group_or<G>(clipped);
+      changed = group_or<G>(changed) | clipped;
+      if (!done && !changed) done = true;
+      KMPC_SYNCWARP();
+      if (warp_any(clipped != 0)) qp_gradient<G>(ws, N);
+    } else {
+      // after a full step: multipliers of the bound variables
+      double worst = INFINITY;
+      int widx = 0x7fffffff;
+      KMPC_LANE_LOOP(i, N) {
+        const int w = ws.W[i];
+        if (w != 0) {
+          const double lam = w < 0 ? ws.grad[i] : -ws.grad[i];
+          if (lam < worst) {
+            worst = lam;
+            widx = i;
+          }
+        }
       }
+      group_argmin<G>(worst, widx);
+      if (!done && !blocked) {
+        if (widx == 0x7fffffff || worst >= -mtol) {
+          done = true;
+        } else if (KMPC_LANE0) {
+          ws.W[widx] = 0;
+        }
+      }
+      KMPC_SYNCWARP();
     }
-    KMPC_SYNCWARP();
   }
   if (!done) status |= KMPC_STATUS_MAXITER;
   int bad = 0;
@@ -575,9 +616,11 @@ KMPC_DEV int spd_right_solve_warp(double* Gm, int n, double* Bm, int rows) {
     }
     KMPC_SYNCWARP();
     double d = Gm[j * n + j];
-    if (!(d > 0.0)) {
+    double orig = d;  // diagonal before elimination = d + sum_k L[j][k]^2
+    for (int k = 0; k < j; ++k) orig += Gm[j * n + k] * Gm[j * n + k];
+    if (!(d > 1e-12 * orig)) {  // (numerically) rank deficient: pinv and inverse differ, flag it
       status |= KMPC_STATUS_PIVOT;
-      d = 1e-300;
+      if (!(d > 0.0)) d = 1e-300;
     }
     const double piv = sqrt(d);
     KMPC_SYNCWARP();

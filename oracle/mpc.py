@@ -98,11 +98,17 @@ def _masked_chol_solve(H2, rhs, free):
 STATUS_MAXITER, STATUS_NONFINITE, STATUS_PIVOT = 1, 2, 4
 
 
-def solve_box_qp_exact(H, f, lb, ub, max_iter=None, tol=1e-10):
-    """Primal active-set method for  min U'HU + f'U,  lb <= U <= ub  (H SPD).
-    Start: clipped unconstrained minimiser with the clipped variables in the working set.
-    Each iteration: Newton step on the free face, ratio test (add the blocking bound) or, after
-    a full step, drop the bound with the most negative multiplier.  Returns U, status, iters."""
+PDAS_ITERS = 8
+
+
+def solve_box_qp_exact(H, f, lb, ub, max_iter=None, tol=1e-10, pdas_iters=PDAS_ITERS):
+    """Exact solve of  min U'HU + f'U,  lb <= U <= ub  (H SPD); the CUDA kernel runs the same steps.
+    Start: clipped unconstrained minimiser, clipped variables in the working set W.
+    Iterations 0..pdas_iters-1 (primal-dual active-set sweeps): full Newton step on the free face,
+    then clip EVERY violated bound into W and release EVERY bound with a negative multiplier; stop
+    when nothing changes (KKT holds exactly).  Later iterations (only if the sweeps cycle): the
+    monotone primal active-set method -- ratio test, add the blocking bound or drop the most negative
+    multiplier -- which always terminates.  Returns U, status, iterations."""
     H = np.asarray(H, dtype=np.float64)
     f = np.asarray(f, dtype=np.float64).reshape(-1)
     N = f.size
@@ -120,43 +126,52 @@ def solve_box_qp_exact(H, f, lb, ub, max_iter=None, tol=1e-10):
     W[x > ub] = 1
     x = np.minimum(np.maximum(x, lb), ub)
     iters = 0
-    if not W.any():
-        if not np.all(np.isfinite(x)):
-            status |= STATUS_NONFINITE
-        return x, status, iters
     mtol = tol * max(1.0, np.max(np.abs(f)))
-    done = False
-    while iters < max_iter:
+    done = not W.any()
+    g = H2 @ x + f
+    while not done and iters < max_iter:
+        pdas = iters < pdas_iters
         iters += 1
-        g = H2 @ x + f
         free = W == 0
         p, ok = _masked_chol_solve(H2, -g, free)
         if not ok:
             status |= STATUS_PIVOT
         alpha, block, side = 1.0, -1, 0
-        for i in range(N):
-            if not free[i]:
-                continue
-            if p[i] > 0.0 and x[i] + p[i] > ub[i]:
-                a = (ub[i] - x[i]) / p[i]
-                if a < alpha:
-                    alpha, block, side = a, i, 1
-            elif p[i] < 0.0 and x[i] + p[i] < lb[i]:
-                a = (lb[i] - x[i]) / p[i]
-                if a < alpha:
-                    alpha, block, side = a, i, -1
+        if not pdas:
+            for i in range(N):
+                if not free[i]:
+                    continue
+                if p[i] > 0.0 and x[i] + p[i] > ub[i]:
+                    a = (ub[i] - x[i]) / p[i]
+                    if a < alpha:
+                        alpha, block, side = a, i, 1
+                elif p[i] < 0.0 and x[i] + p[i] < lb[i]:
+                    a = (lb[i] - x[i]) / p[i]
+                    if a < alpha:
+                        alpha, block, side = a, i, -1
         x = x + alpha * p
         if block >= 0:
             x[block] = ub[block] if side > 0 else lb[block]
             W[block] = side
-            continue
         g = H2 @ x + f
-        lam = np.where(W < 0, g, np.where(W > 0, -g, np.inf))
-        worst = int(np.argmin(lam))
-        if lam[worst] >= -mtol:
-            done = True
-            break
-        W[worst] = 0
+        if pdas:
+            lam = np.where(W < 0, g, np.where(W > 0, -g, np.inf))
+            release = lam < -mtol                      # multipliers at the face minimiser
+            lo, hi = free & (x < lb), free & (x > ub)  # violated bounds of the free variables
+            W[release] = 0
+            W[lo], W[hi] = -1, 1
+            x[lo], x[hi] = lb[lo], ub[hi]
+            if not (release.any() or lo.any() or hi.any()):
+                done = True
+            elif lo.any() or hi.any():
+                g = H2 @ x + f
+        elif block < 0:
+            lam = np.where(W < 0, g, np.where(W > 0, -g, np.inf))
+            worst = int(np.argmin(lam))
+            if lam[worst] >= -mtol:
+                done = True
+            else:
+                W[worst] = 0
     if not done:
         status |= STATUS_MAXITER
     if not np.all(np.isfinite(x)):
