@@ -21,6 +21,8 @@ template <int G, int NZ, int N, int OUT, int DU>
 __global__ void __launch_bounds__(kLoopThreads)
 loop_qp_plant_kernel(LoopDev d, int64_t step, int64_t log_slot) {
   extern __shared__ double smem[];
+  pdl_wait();  // everything this kernel reads (A, B, C, z, x) comes from the previous kernels
+  pdl_launch_dependents();
   const int group = threadIdx.x / G;
   int64_t s = (int64_t)blockIdx.x * (blockDim.x / G) + group;
   const bool valid = s < d.c.S;
@@ -34,7 +36,7 @@ loop_qp_plant_kernel(LoopDev d, int64_t step, int64_t log_slot) {
   const int nzq = sh.nz + sh.du_aug;
   const bool identity = sh.out_mode == KMPC_OUT_IDENTITY;
   const int ny = identity ? nzq : (sh.out_mode == KMPC_OUT_C ? 2 : 1);
-  loop_qp_plant_scenario<G>(d, sh, s, valid, step, log_slot,
+  loop_qp_plant_scenario<G, (NZ > 0 && N + 1 <= G) ? N : 0>(d, sh, s, valid, step, log_slot,
                             smem + (size_t)group * qp_ws_doubles(nzq, ny, sh.N, identity));
 }
 
@@ -182,7 +184,7 @@ static int run_one_step(kmpc_ctx* ctx, void* stream, cudaEvent_t* ev) {
   const unsigned rls_grid = (unsigned)((c.S + L.rls_spb - 1) / L.rls_spb);
   const int64_t slot = (ctx->step < ctx->d.b.log_capacity) ? ctx->step : -1;
   if (ev) KMPC_CUDA(cudaEventRecord(ev[0], st));
-  L.qp<<<qp_grid, L.qp_spb * L.qp_g, L.qp_smem, st>>>(ctx->d, ctx->step, slot);
+  KMPC_CUDA(launch_pdl(L.qp, qp_grid, (unsigned)(L.qp_spb * L.qp_g), (size_t)L.qp_smem, st, ctx->d, ctx->step, slot));
   KMPC_AFTER_LAUNCH();
   if (ev) KMPC_CUDA(cudaEventRecord(ev[1], st));
   // lift(x+): into z_next when the RLS still needs the old z, else straight into z
@@ -195,7 +197,8 @@ static int run_one_step(kmpc_ctx* ctx, void* stream, cudaEvent_t* ev) {
   if (rc != KMPC_OK) return rc;
   if (ev) KMPC_CUDA(cudaEventRecord(ev[2], st));
   if (c.update) {
-    L.rls<<<rls_grid, L.rls_spb * L.rls_g, L.rls_smem, st>>>(ctx->d, ctx->rls_started ? 0 : 1);
+    KMPC_CUDA(launch_pdl(L.rls, rls_grid, (unsigned)(L.rls_spb * L.rls_g), (size_t)L.rls_smem, st, ctx->d,
+                         ctx->rls_started ? 0 : 1));
     KMPC_AFTER_LAUNCH();
     ctx->rls_started = 1;
   }

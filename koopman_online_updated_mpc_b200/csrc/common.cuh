@@ -40,6 +40,34 @@ inline cudaError_t ensure_smem(K kernel, int bytes) {
 
 constexpr int kWarpsPerBlock = 4;
 
+// ---- programmatic dependent launch (PDL): the next kernel of the step is launched while the
+// current one is still running; it may do work that does not depend on its predecessor (weight
+// staging, RLS state loads) and then blocks in pdl_wait() until the predecessor has completed and
+// its writes are visible.  Every kernel triggers its successor only AFTER its own wait, so a
+// prologue can overlap the immediate predecessor only.  SASS: ACQBULK / PREEXIT.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                              cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // how many warps (each with `doubles_per_warp` of workspace) fit in a block's shared memory
 inline int warps_that_fit(int doubles_per_warp) {
   const int budget = 200 * 1024;

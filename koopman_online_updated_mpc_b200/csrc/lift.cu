@@ -196,6 +196,9 @@ encoder_mma_kernel(EncParams p, const double* __restrict__ x, double* __restrict
       }
     }
   }
+  // the weight copies above do not depend on the previous kernel: only now wait for it (PDL)
+  pdl_wait();
+  pdl_launch_dependents();
   const int n = p.dims[0];
   const int off = (lift_mode == KMPC_LIFT_STACK) ? n : 0;
   const int gid = lane >> 2, tig = lane & 3;   // mma fragment coordinates
@@ -351,7 +354,8 @@ static int launch_encoder(const kmpc_encoder* enc, const double* x, double* z, i
   if (enc->smem_bytes > 0) {
     KMPC_CUDA(ensure_smem(encoder_mma_kernel, enc->smem_bytes));
     const unsigned grid = (unsigned)(tiles < enc->num_sms ? tiles : enc->num_sms);
-    encoder_mma_kernel<<<grid, kMmaThreads, enc->smem_bytes, st>>>(enc->p, x, z, S, lift_mode, out_dim, tiles);
+    KMPC_CUDA(launch_pdl(encoder_mma_kernel, grid, (unsigned)kMmaThreads, (size_t)enc->smem_bytes, st, enc->p, x, z,
+                         S, lift_mode, out_dim, tiles));
   } else {
     const int smem = 2 * KMPC_MAX_WIDTH * kTileS * (int)sizeof(double);
     KMPC_CUDA(ensure_smem(encoder_kernel, smem));

@@ -30,7 +30,8 @@ KMPC_HD inline LoopShape loop_shape(const kmpc_loop_config& c) {
 
 // QP + plant for scenario s at closed-loop step `step`; `base` = this group's smem slice;
 // `valid` = false for the padding groups of the last warp (compute, but write nothing).
-template <int G>
+// NFAST > 0 (== the horizon, compile time, NFAST + 1 <= G) selects the register-resident QP solve.
+template <int G, int NFAST = 0>
 KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, const LoopShape sh, int64_t s, bool valid,
                                      int64_t step, int64_t log_slot, double* base) {
   const kmpc_loop_config& c = d.c;
@@ -74,7 +75,12 @@ KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, const LoopShape sh, int64
   }
   KMPC_SYNCWARP();
   qp_build_warp<G>(ws, nzq, ny, N, identity, c.q, c.rw, d.b.r + s * ny, 0, nullptr);
+#ifndef KMPC_HOSTEMU
+  const int st = (NFAST > 0) ? qp_solve_fast<G, (NFAST > 0 ? NFAST : 1)>(ws, c.max_iter, c.tol)
+                             : qp_solve_warp<G>(ws, N, c.max_iter, c.tol);
+#else
   const int st = qp_solve_warp<G>(ws, N, c.max_iter, c.tol);
+#endif
   if (KMPC_LANE0 && valid) {
     const double move = ws.x[0];
     const double u = sh.du_aug ? uprev + move : move;
@@ -121,6 +127,9 @@ KMPC_DEV void loop_rls_scenario(const LoopDev& d, const int nz, int64_t s, bool 
       KMPC_LANE_LOOP(e, nz * nz) ws.barQ[e] = d.b.barQ[s * nz * nz + e];
     }
   }
+  // the RLS state above is not touched by the QP / lift kernels of this step, so it was loaded
+  // before waiting on them (programmatic dependent launch); the sample below is their output
+  KMPC_PDL_WAIT();
   KMPC_LANE_LOOP(e, nz) {
     ws.v[e] = d.b.z[s * nz + e];
     ws.y[e] = d.z_next[s * nz + e];

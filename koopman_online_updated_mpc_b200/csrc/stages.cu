@@ -46,6 +46,8 @@ rls_update_kernel(double* __restrict__ KA, double* __restrict__ P, double* __res
 }
 
 // ------------------------------------------------------------------------------ QP -----------
+// G lanes per scenario; NFAST > 0: compile-time horizon with the register-resident solve.
+template <int G, int NFAST>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 qp_first_move_kernel(const double* __restrict__ A, const double* __restrict__ B,
                      const double* __restrict__ Cy, const double* __restrict__ z0,
@@ -55,36 +57,40 @@ qp_first_move_kernel(const double* __restrict__ A, const double* __restrict__ B,
                      double* __restrict__ u0, double* __restrict__ Ufull, int* __restrict__ status,
                      int max_iter, double tol) {
   extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (s >= S) return;
+  const int group = threadIdx.x / G, lane = threadIdx.x & (G - 1);
+  int64_t s = (int64_t)blockIdx.x * (blockDim.x / G) + group;
+  const bool valid = s < S;
+  if (!valid) s = S - 1;
+  if (NFAST > 0) N = NFAST;
   const bool identity = flags & KMPC_QP_CY_IDENTITY;
   const bool shared_model = flags & KMPC_QP_SHARED_MODEL;
   const bool r_full = flags & KMPC_QP_R_FULL;
-  QpWs ws = qp_ws_carve(smem + (size_t)warp * qp_ws_doubles(nz, ny, N, identity), nz, ny, N, identity);
+  QpWs ws = qp_ws_carve(smem + (size_t)group * qp_ws_doubles(nz, ny, N, identity), nz, ny, N, identity);
   const int64_t sm = shared_model ? 0 : s;
-  for (int e = lane; e < nz * nz; e += 32) ws.A[e] = A[sm * nz * nz + e];
-  for (int e = lane; e < nz; e += 32) {
+  for (int e = lane; e < nz * nz; e += G) ws.A[e] = A[sm * nz * nz + e];
+  for (int e = lane; e < nz; e += G) {
     ws.B[e] = B[sm * nz + e];
     ws.z0[e] = z0[s * nz + e];
   }
   if (!identity)
-    for (int e = lane; e < ny * nz; e += 32) ws.Cy[e] = Cy[sm * ny * nz + e];
-  for (int e = lane; e < N; e += 32) {
+    for (int e = lane; e < ny * nz; e += G) ws.Cy[e] = Cy[sm * ny * nz + e];
+  for (int e = lane; e < N; e += G) {
     ws.lb[e] = lb[s * N + e];
     ws.ub[e] = ub[s * N + e];
   }
   __syncwarp();
   const double* rs = r_full ? r + s * N * ny : r + s * ny;
   const double* pn = PN ? PN + sm * ny * ny : nullptr;
-  qp_build_warp<32>(ws, nz, ny, N, identity, q, rw, rs, r_full ? ny : 0, pn);
-  const int st = qp_solve_warp<32>(ws, N, max_iter, tol);
+  qp_build_warp<G>(ws, nz, ny, N, identity, q, rw, rs, r_full ? ny : 0, pn);
+  const int st = (NFAST > 0) ? qp_solve_fast<G, (NFAST > 0 ? NFAST : 1)>(ws, max_iter, tol)
+                             : qp_solve_warp<G>(ws, N, max_iter, tol);
+  if (!valid) return;
   if (lane == 0) {
     u0[s] = ws.x[0];
     if (status) status[s] = st;
   }
   if (Ufull)
-    for (int e = lane; e < N; e += 32) Ufull[s * N + e] = ws.x[e];
+    for (int e = lane; e < N; e += G) Ufull[s * N + e] = ws.x[e];
 }
 
 // ------------------------------------------------------------------------------ plant --------
@@ -105,6 +111,8 @@ __global__ void plant_step_kernel(const double* __restrict__ x, const double* __
 // ------------------------------------------------------------------------------ RBF ----------
 __global__ void rbf_lift_kernel(const double* __restrict__ x, const double* __restrict__ cx,
                                 double* __restrict__ z, int64_t S, int n, int nz, int variant) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= S * nz) return;
   const int64_t s = e / nz;
@@ -152,13 +160,27 @@ int kmpc_qp_first_move(const double* A, const double* B, const double* Cy, const
   if (!identity && !Cy) return KMPC_ERR_ARG;
   if (max_iter <= 0) max_iter = 10 * N + 20;
   if (!(tol > 0.0)) tol = 1e-10;
-  const int wpb = warps_that_fit(qp_ws_doubles(nz, ny, N, identity));
-  if (wpb < 1) return KMPC_ERR_UNSUPPORTED;
-  const int smem = wpb * qp_ws_doubles(nz, ny, N, identity) * (int)sizeof(double);
-  KMPC_CUDA(ensure_smem(qp_first_move_kernel, smem));
-  const unsigned grid = (unsigned)((S + wpb - 1) / wpb);
-  qp_first_move_kernel<<<grid, wpb * 32, smem, as_stream(stream)>>>(
-      A, B, Cy, z0, r, lb, ub, PN, q, rw, N, ny, nz, S, flags, u0, Ufull, status, max_iter, tol);
+  // horizons 10 (duffing.py / vanderpol.py) and 20 (Tank_System.m) have register-resident solves
+  typedef void (*Kern)(const double*, const double*, const double*, const double*, const double*,
+                       const double*, const double*, const double*, double, double, int, int, int,
+                       int64_t, int, double*, double*, int*, int, double);
+  Kern kern = qp_first_move_kernel<32, 0>;
+  int g = 32;
+  if (N == 10) {
+    kern = qp_first_move_kernel<16, 10>;
+    g = 16;
+  } else if (N == 20) {
+    kern = qp_first_move_kernel<32, 20>;
+  }
+  const int ws_bytes = qp_ws_doubles(nz, ny, N, identity) * (int)sizeof(double);
+  int spb = (kWarpsPerBlock * 32) / g;
+  while (spb > 32 / g && spb * ws_bytes > 200 * 1024) spb >>= 1;
+  if (spb * ws_bytes > 200 * 1024) return KMPC_ERR_UNSUPPORTED;
+  const int smem = spb * ws_bytes;
+  KMPC_CUDA(ensure_smem(kern, smem));
+  const unsigned grid = (unsigned)((S + spb - 1) / spb);
+  kern<<<grid, spb * g, smem, as_stream(stream)>>>(A, B, Cy, z0, r, lb, ub, PN, q, rw, N, ny, nz, S, flags, u0,
+                                                  Ufull, status, max_iter, tol);
   KMPC_AFTER_LAUNCH();
   return KMPC_OK;
 }
@@ -183,7 +205,7 @@ int kmpc_rbf_lift(const double* x, const double* cx, double* z, int64_t S, int n
   if (!x || !cx || !z) return KMPC_ERR_ARG;
   const int64_t total = S * nz;
   const unsigned grid = (unsigned)((total + 255) / 256);
-  rbf_lift_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, cx, z, S, n, nz, variant);
+  KMPC_CUDA(launch_pdl(rbf_lift_kernel, grid, 256u, (size_t)0, as_stream(stream), x, cx, z, S, n, nz, variant));
   KMPC_AFTER_LAUNCH();
   return KMPC_OK;
 }
