@@ -17,7 +17,7 @@ constexpr int kLoopThreads = 128;
 
 // G lanes per scenario; NZ/N/OUT/DU > 0 give a compile-time QP shape (loops unrolled, indices
 // folded), NZ == 0 reads the shape from the config at run time.
-template <int G, int NZ, int N, int OUT, int DU>
+template <int G, int NZ, int N, int OUT, int DU, bool FAST = true>
 __global__ void __launch_bounds__(kLoopThreads)
 loop_qp_plant_kernel(LoopDev d, int64_t step, int64_t log_slot) {
   extern __shared__ double smem[];
@@ -36,7 +36,7 @@ loop_qp_plant_kernel(LoopDev d, int64_t step, int64_t log_slot) {
   const int nzq = sh.nz + sh.du_aug;
   const bool identity = sh.out_mode == KMPC_OUT_IDENTITY;
   const int ny = identity ? nzq : (sh.out_mode == KMPC_OUT_C ? 2 : 1);
-  loop_qp_plant_scenario<G, (NZ > 0 && N + 1 <= G) ? N : 0>(d, sh, s, valid, step, log_slot,
+  loop_qp_plant_scenario<G, (FAST && NZ > 0 && N + 1 <= G) ? N : 0>(d, sh, s, valid, step, log_slot,
                             smem + (size_t)group * qp_ws_doubles(nzq, ny, sh.N, identity));
 }
 
@@ -67,7 +67,16 @@ static bool select_launch(const kmpc_loop_config& c, LoopLaunch* L) {
   const bool identity = c.out_mode == KMPC_OUT_IDENTITY;
   const int ny = identity ? nzq : (c.out_mode == KMPC_OUT_C ? 2 : 1);
   L->qp_g = 32;
-  if (c.nz == 8 && c.N == 10 && !c.du_aug && c.out_mode == KMPC_OUT_IDENTITY) {
+  const bool fast = qp_fast_enabled();
+  if (!fast && c.nz == 8 && c.N == 10 && !c.du_aug && c.out_mode == KMPC_OUT_IDENTITY) {
+    L->qp = loop_qp_plant_kernel<16, 8, 10, KMPC_OUT_IDENTITY, 0, false>;
+    L->qp_g = 16;
+  } else if (!fast && c.nz == 8 && c.N == 10 && !c.du_aug && c.out_mode == KMPC_OUT_C) {
+    L->qp = loop_qp_plant_kernel<16, 8, 10, KMPC_OUT_C, 0, false>;
+    L->qp_g = 16;
+  } else if (!fast && c.nz == 10 && c.N == 20 && c.du_aug && c.out_mode == KMPC_OUT_C_ROW) {
+    L->qp = loop_qp_plant_kernel<32, 10, 20, KMPC_OUT_C_ROW, 1, false>;
+  } else if (c.nz == 8 && c.N == 10 && !c.du_aug && c.out_mode == KMPC_OUT_IDENTITY) {
     L->qp = loop_qp_plant_kernel<16, 8, 10, KMPC_OUT_IDENTITY, 0>;   // vanderpol.py
     L->qp_g = 16;
   } else if (c.nz == 8 && c.N == 10 && !c.du_aug && c.out_mode == KMPC_OUT_C) {

@@ -166,10 +166,13 @@ int kmpc_qp_first_move(const double* A, const double* B, const double* Cy, const
                        int64_t, int, double*, double*, int*, int, double);
   Kern kern = qp_first_move_kernel<32, 0>;
   int g = 32;
-  if (N == 10) {
+  if (N == 10 && !qp_fast_enabled()) {
+    kern = qp_first_move_kernel<16, 0>;
+    g = 16;
+  } else if (N == 10) {
     kern = qp_first_move_kernel<16, 10>;
     g = 16;
-  } else if (N == 20) {
+  } else if (N == 20 && qp_fast_enabled()) {
     kern = qp_first_move_kernel<32, 20>;
   }
   const int ws_bytes = qp_ws_doubles(nz, ny, N, identity) * (int)sizeof(double);
