@@ -5,7 +5,7 @@ repository (MichaelMillerCSU/Koopman-online-updated-MPC), each function citing t
 file:line it follows.  It exists so that the CUDA product path can be checked against the
 reference's arithmetic on machines that have neither the reference nor MATLAB.
 
-Rules (enforced by tests/test_layout.py):
+Rules (enforced by tests/test_abi.py::test_package_never_imports_the_oracle):
   * only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
     `bench.py` may import this package -- and only as the checker / the timed CPU baseline;
   * nothing under `koopman_online_updated_mpc_b200/` imports it; the product has no CPU
