@@ -1,24 +1,36 @@
 """Build libkmpc.so in-tree with nvcc for sm_100a (B200).  No JIT cache, no torch extension
-machinery: the library is a plain C-ABI shared object (include/kmpc.h) loaded with ctypes."""
+machinery: the library is a plain C-ABI shared object (include/kmpc.h) loaded with ctypes.
+Translation units are compiled in parallel into csrc/_obj/*.o (rebuilt only when stale) and
+linked with nvcc -shared."""
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
+OBJ_DIR = os.path.join(CSRC, "_obj")
 LIB_PATH = os.path.join(PKG_DIR, "libkmpc.so")
-SOURCES = ["abi.cu", "stages.cu", "lift.cu", "edmd.cu", "closed_loop.cu"]
-NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-O3", "-lineinfo", "-std=c++17",
+SOURCES = ["abi.cu", "stages.cu", "lift.cu", "edmd.cu", "closed_loop.cu", "fused.cu"]
+NVCC_FLAGS = ["-Xcompiler", "-fPIC", "-O3", "-lineinfo", "-std=c++17",
               "-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(PKG_DIR, "..", "include", "kmpc.h"))
+    return hs
+
+
+def _newest(paths):
+    return max(os.path.getmtime(p) for p in paths)
 
 
 def _stale():
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps.append(os.path.join(PKG_DIR, "..", "include", "kmpc.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + _headers()
+    return _newest(deps) > os.path.getmtime(LIB_PATH)
 
 
 def build(force=False, verbose=False):
@@ -26,7 +38,24 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr_time = _newest(_headers())
+
+    def compile_one(src):
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        if (not force and os.path.exists(o)
+                and os.path.getmtime(o) > max(os.path.getmtime(s), hdr_time)):
+            return o
+        cmd = [nvcc, "-c"] + NVCC_FLAGS + ["-o", o, s]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        return o
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

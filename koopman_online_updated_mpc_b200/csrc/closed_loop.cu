@@ -13,6 +13,11 @@
 
 namespace kmpc {
 
+// fused.cu: the persistent kernel for nz = 8, N = 10 loops
+bool fused_eligible(const kmpc_loop_config& c, const kmpc_encoder* enc);
+int fused_launch(const LoopDev& d, const kmpc_encoder* enc, int64_t step0, int T, int first,
+                 long long* timing, int* grid_out, cudaStream_t st);
+
 constexpr int kLoopThreads = 128;
 
 // G lanes per scenario; NZ/N/OUT/DU > 0 give a compile-time QP shape (loops unrolled, indices
@@ -115,13 +120,14 @@ struct kmpc_ctx {
   int64_t step;
   int rls_started;
   LoopLaunch launch;
+  bool fused;               // T steps per launch through fused_loop_kernel
+  long long* d_timing;      // fused + timed: per-CTA phase cycle counters (allocated on first use)
 };
 
 extern "C" {
 
 int kmpc_ctx_create(kmpc_ctx** out, const kmpc_loop_config* cfg, const kmpc_loop_buffers* buf,
                     const kmpc_encoder* enc, int rls_started, void* stream) {
-  (void)stream;
   if (!out || !cfg || !buf) return KMPC_ERR_ARG;
   const kmpc_loop_config& c = *cfg;
   if (c.S < 1 || c.n != 2 || c.nz < 1 || c.N < 1 || c.N > KMPC_MAX_HORIZON) return KMPC_ERR_ARG;
@@ -154,8 +160,16 @@ int kmpc_ctx_create(kmpc_ctx** out, const kmpc_loop_config* cfg, const kmpc_loop
   ctx->rls_started = rls_started;
   ctx->d.z_next = nullptr;
   ctx->d.x_prev = nullptr;
+  ctx->d_timing = nullptr;
+  ctx->d.wset = nullptr;
+  ctx->fused = fused_eligible(ctx->d.c, enc);
   if (cudaMalloc(&ctx->d.z_next, (size_t)c.S * c.nz * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&ctx->d.x_prev, (size_t)c.S * c.n * sizeof(double)) != cudaSuccess) {
+    kmpc_ctx_destroy(ctx);
+    return KMPC_ERR_ALLOC;
+  }
+  if (ctx->fused && (cudaMalloc(&ctx->d.wset, (size_t)c.S * 2 * sizeof(unsigned int)) != cudaSuccess ||
+                     cudaMemsetAsync(ctx->d.wset, 0, (size_t)c.S * 2 * sizeof(unsigned int), as_stream(stream)) != cudaSuccess)) {
     kmpc_ctx_destroy(ctx);
     return KMPC_ERR_ALLOC;
   }
@@ -177,6 +191,8 @@ int kmpc_ctx_destroy(kmpc_ctx* ctx) {
   if (!ctx) return KMPC_OK;
   if (ctx->d.z_next) cudaFree(ctx->d.z_next);
   if (ctx->d.x_prev) cudaFree(ctx->d.x_prev);
+  if (ctx->d_timing) cudaFree(ctx->d_timing);
+  if (ctx->d.wset) cudaFree(ctx->d.wset);
   delete ctx;
   return KMPC_OK;
 }
@@ -216,8 +232,19 @@ static int run_one_step(kmpc_ctx* ctx, void* stream, cudaEvent_t* ev) {
   return KMPC_OK;
 }
 
+static int run_fused(kmpc_ctx* ctx, int T, long long* timing, int* grid, void* stream) {
+  if (T == 0) return KMPC_OK;
+  const int first = (ctx->d.c.update && !ctx->rls_started) ? 1 : 0;
+  const int rc = fused_launch(ctx->d, ctx->enc, ctx->step, T, first, timing, grid, as_stream(stream));
+  if (rc != KMPC_OK) return rc;
+  if (ctx->d.c.update) ctx->rls_started = 1;
+  ctx->step += T;
+  return KMPC_OK;
+}
+
 int kmpc_closed_loop_steps(kmpc_ctx* ctx, int T, void* stream) {
   if (!ctx || T < 0) return KMPC_ERR_ARG;
+  if (ctx->fused) return run_fused(ctx, T, nullptr, nullptr, stream);
   for (int t = 0; t < T; ++t) {
     const int rc = run_one_step(ctx, stream, nullptr);
     if (rc != KMPC_OK) return rc;
@@ -226,7 +253,45 @@ int kmpc_closed_loop_steps(kmpc_ctx* ctx, int T, void* stream) {
 }
 
 int kmpc_closed_loop_steps_timed(kmpc_ctx* ctx, int T, void* stream, float* ms) {
-  if (!ctx || T < 1 || T > 1024 || !ms) return KMPC_ERR_ARG;
+  if (!ctx || T < 1 || !ms) return KMPC_ERR_ARG;
+  if (ctx->fused) {
+    // one launch; the kernel accumulates clock64() per phase in every CTA, the launch itself is
+    // bracketed by CUDA events: ms[k] = launch time x mean over CTAs of the phase's cycle share
+    const int kMaxCtas = 4096;
+    if (!ctx->d_timing && cudaMalloc(&ctx->d_timing, sizeof(long long) * 4 * kMaxCtas) != cudaSuccess)
+      return KMPC_ERR_ALLOC;
+    cudaStream_t st = as_stream(stream);
+    cudaEvent_t e0, e1;
+    KMPC_CUDA(cudaEventCreate(&e0));
+    KMPC_CUDA(cudaEventCreate(&e1));
+    KMPC_CUDA(cudaEventRecord(e0, st));
+    int grid = 0;
+    int rc = run_fused(ctx, T, ctx->d_timing, &grid, stream);
+    if (rc == KMPC_OK && cudaEventRecord(e1, st) != cudaSuccess) rc = KMPC_ERR_CUDA;
+    if (rc == KMPC_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = KMPC_ERR_CUDA;
+    ms[0] = ms[1] = ms[2] = 0.f;
+    if (rc == KMPC_OK) {
+      float total = 0.f;
+      cudaEventElapsedTime(&total, e0, e1);
+      std::vector<long long> h((size_t)4 * grid);
+      if (cudaMemcpy(h.data(), ctx->d_timing, sizeof(long long) * 4 * grid, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = KMPC_ERR_CUDA;
+      double share[3] = {0, 0, 0};
+      for (int i = 0; rc == KMPC_OK && i < grid; ++i)
+        for (int k = 0; k < 3; ++k) share[k] += (double)h[4 * i + k] / (double)(h[4 * i + 3] > 0 ? h[4 * i + 3] : 1);
+      for (int k = 0; k < 3; ++k) ms[k] = (float)(total * share[k] / (grid > 0 ? grid : 1));
+      if (rc == KMPC_OK && getenv("KMPC_DEBUG_TIMING")) {
+        long long mx = 0;
+        for (int i = 0; i < grid; ++i) mx = h[4 * i + 3] > mx ? h[4 * i + 3] : mx;
+        fprintf(stderr, "[kmpc] fused timed: grid %d, T %d, %.3f ms, max CTA cycles %lld -> SM clock %.0f MHz\n",
+                grid, T, total, mx, mx / (total * 1e3));
+      }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+  }
+  if (T > 1024) return KMPC_ERR_ARG;
   std::vector<cudaEvent_t> ev((size_t)4 * T);
   for (auto& e : ev) KMPC_CUDA(cudaEventCreate(&e));
   int rc = KMPC_OK;

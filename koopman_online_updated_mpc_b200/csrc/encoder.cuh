@@ -1,0 +1,196 @@
+// encoder.cuh -- theta_E encoder pieces shared by lift.cu (stand-alone lift kernels) and fused.cu
+// (the persistent closed-loop kernel): packed weight layout, TMA bulk-copy / mbarrier helpers and
+// the per-tile layer chain on the fp64 tensor path (mma.sync m8n8k4 f64).
+//
+// Reference: duffing.py:21-29 (`nn.Sequential(Linear(2,100), ReLU, Linear(100,100), ReLU,
+// Linear(100,100), ReLU, Linear(100,8))`), Encoder_Tank.m:3-5 (3 layers, nz = 10).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace kmpc {
+
+constexpr int kTileS = 32;         // scenarios (rows) per CTA tile
+constexpr int kMmaWarps = 8;
+constexpr int kMmaThreads = kMmaWarps * 32;
+constexpr int kActStride = 36;     // doubles per activation row k: 32 scenarios + 4 pad (== 4 mod 16)
+
+struct EncParams {
+  int n_layers;
+  int dims[KMPC_MAX_LAYERS + 1];
+  int pad[KMPC_MAX_LAYERS + 1];
+  const double* wt[KMPC_MAX_LAYERS];
+  const double* b[KMPC_MAX_LAYERS];
+  const double* z0;
+  const double* packed;            // [W1t | b1 | W2t | b2 | ...] (same layout as the smem copy)
+  int woff[KMPC_MAX_LAYERS];       // offset (doubles) of layer l's W block inside `packed`
+  int wlen[KMPC_MAX_LAYERS];       // doubles of layer l's W + bias block
+  int total_w;                     // doubles in `packed`
+  int actw;                        // activation buffer width (max padded layer width)
+  int wstride[KMPC_MAX_LAYERS];    // row stride (doubles) of layer l's W^T block, == 4 (mod 16)
+  int inpad[KMPC_MAX_LAYERS];      // rows of layer l's W^T block (in rounded up to 4, zero rows)
+};
+
+#ifdef __CUDACC__
+// ---- TMA bulk-copy / mbarrier helpers (PTX; SASS: UBLKCP, SYNCS) --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Thread 0 of the CTA: initialise one mbarrier per layer and start the TMA bulk copies of the
+// packed weight set into `wsm`.  Callers __syncthreads() between the init and the issue.
+__device__ __forceinline__ void encoder_weights_init_barriers(const EncParams& p, uint64_t* bars) {
+  for (int l = 0; l < p.n_layers; ++l) mbar_init(&bars[l], 1);
+  mbar_fence_init();
+}
+__device__ __forceinline__ void encoder_weights_issue(const EncParams& p, double* wsm, uint64_t* bars) {
+  for (int l = 0; l < p.n_layers; ++l) {
+    const uint32_t bytes = (uint32_t)p.wlen[l] * 8u;
+    mbar_expect_tx(&bars[l], bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768u) {
+      const uint32_t sz = (bytes - o < 32768u) ? (bytes - o) : 32768u;
+      bulk_copy_g2s(reinterpret_cast<char*>(wsm + p.woff[l]) + o,
+                    reinterpret_cast<const char*>(p.packed + p.woff[l]) + o, sz, &bars[l]);
+    }
+  }
+}
+
+// k-loop of one layer for a warp that owns NT n-tiles (two m-tiles each): 2 NT DMMAs per k-step
+template <int NT>
+__device__ __forceinline__ void encoder_kloop(const double* __restrict__ ap, const double* __restrict__ bp,
+                                              int kin, int ws, double (&c)[2][4][2]) {
+#pragma unroll 2
+  for (int k0 = 0; k0 < kin; k0 += 4) {
+    const double a0 = ap[k0 * kActStride];
+    const double a1 = ap[k0 * kActStride + 8];
+    double b[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) b[j] = bp[k0 * ws + 32 * j];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      dmma_m8n8k4(c[0][j][0], c[0][j][1], a0, b[j]);
+      dmma_m8n8k4(c[1][j][0], c[1][j][1], a1, b[j]);
+    }
+  }
+}
+
+// All layers of one 32-row tile.  The layer-0 input must already be in `in0` (k-major,
+// in0[k * kActStride + row], rows [n, inpad[0]) zero; may be `act` itself) and visible
+// (__syncthreads() by the caller).
+// Warp w owns rows 16*(w&1)..+15 (two m-tiles) and the n-tiles {w>>1, (w>>1)+4, ...} of every
+// layer; activations are rewritten in place between two barriers.  Final outputs are handed to
+// store(row_in_tile, col, value) (before the subtraction of theta(0), which the caller applies).
+// Ends with a __syncthreads(): `act` is free and the stores of all warps are done.
+template <typename Store>
+__device__ __forceinline__ void encoder_layers(const EncParams& p, const double* in0, double* act,
+                                               const double* wsm, uint64_t* bars, Store store) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;   // mma fragment coordinates
+  const int mrow = 16 * (warp & 1);            // first row of this warp's two m-tiles
+  const int ng = warp >> 1;                    // n-tile group
+  for (int l = 0; l < p.n_layers; ++l) {
+    const int kin = p.inpad[l], out = p.dims[l + 1], ws = p.wstride[l];
+    const int nt = (out + 7) >> 3;
+    const bool last = (l == p.n_layers - 1);
+    mbar_wait(&bars[l], 0);  // layer l's weights have landed (returns at once after the first tile)
+    const double* wt = wsm + p.woff[l];
+    const double* bias = wt + kin * ws;
+    double c[2][4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n0 = (ng + 4 * j) * 8;
+      const double b0 = (ng + 4 * j < nt) ? bias[n0 + 2 * tig] : 0.0;
+      const double b1 = (ng + 4 * j < nt) ? bias[n0 + 2 * tig + 1] : 0.0;
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        c[m][j][0] = b0;
+        c[m][j][1] = b1;
+      }
+    }
+    const double* ap = (l == 0 ? in0 : act) + tig * kActStride + mrow + gid;
+    const double* bp = wt + tig * ws + ng * 8 + gid;
+    // number of n-tiles this warp owns in this layer (warp-uniform): the k-loop is instantiated per
+    // count so that no DMMA is predicated (a predicated DMMA costs ~27 instead of 16 cycles)
+    const int my_nt = (nt > ng) ? ((nt - ng + 3) >> 2) : 0;
+    switch (my_nt) {
+      case 4: encoder_kloop<4>(ap, bp, kin, ws, c); break;
+      case 3: encoder_kloop<3>(ap, bp, kin, ws, c); break;
+      case 2: encoder_kloop<2>(ap, bp, kin, ws, c); break;
+      case 1: encoder_kloop<1>(ap, bp, kin, ws, c); break;
+      default: break;
+    }
+    __syncthreads();  // every warp has finished reading the activations of this layer
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (ng + 4 * j < nt) {
+        const int col = (ng + 4 * j) * 8 + 2 * tig;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const int r = mrow + 8 * m + gid;
+          if (!last) {
+            act[col * kActStride + r] = fmax(c[m][j][0], 0.0);
+            act[(col + 1) * kActStride + r] = fmax(c[m][j][1], 0.0);
+          } else {
+            if (col < out) store(r, col, c[m][j][0]);
+            if (col + 1 < out) store(r, col + 1, c[m][j][1]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace kmpc
+
+// the opaque handle of include/kmpc.h
+struct kmpc_encoder {
+  kmpc::EncParams p;
+  int smem_bytes = 0;      // dynamic smem of encoder_mma_kernel (0: does not fit, use the fallback)
+  int num_sms = 148;
+  int max_smem_optin = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin
+  std::vector<double*> owned;
+  double* d_z0 = nullptr;
+  // L2-resident lift workspace for kmpc_gram_from_snapshots (allocated on first use)
+  double* d_ws = nullptr;
+  int64_t ws_rows = 0;
+};

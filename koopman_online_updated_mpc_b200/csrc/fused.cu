@@ -1,0 +1,887 @@
+// fused.cu -- the persistent fused closed-loop kernel (nz = 8, horizon 10: duffing.py,
+// vanderpol.py, duffing_RBF.py shapes).
+//
+// ONE launch runs T closed-loop steps of every scenario (duffing.py:823-992 loop body):
+//     z = lift(x) -> condensed box-QP -> u -> x+ = plant(x, u) -> y = lift(x+) -> RLS(z,u,y) -> A,B,C
+// A CTA owns a tile of 32 scenarios for all T steps; 8 lanes own one scenario.  Everything a
+// scenario carries from step to step -- the model A, B, C, the lift z, the plant state and the RLS
+// state K_A, P, bar_X, bar_Q (233 doubles) -- lives in the REGISTERS of its 8 lanes, distributed by
+// rows (lane i holds row i), and touches HBM once per launch instead of once per step.  The
+// encoder weights (182 KB) are brought into shared memory once per CTA by the TMA engine and the
+// 32 x (2-100-100-100-8) MLP of a step runs on the fp64 tensor path (encoder.cuh).  Per-scenario
+// scratch (184 doubles) aliases the encoder's activation buffer: the phases of a step are
+// separated by CTA barriers.
+//
+// Step schedule of a CTA (8 warps, warp w = scenarios 4w..4w+3):
+//   QP build   lanes cooperate: Krylov chains VZ[t] = A^(t+1) z, VB[t] = A^t B (lane i = component
+//              i, vectors exchanged through shared memory), then H = q G'G + rw I and
+//              f = 2 q G'(F z - r) from lane-local partial sums reduced across the 8 lanes;
+//   QP solve   lane 0 of the scenario: exact primal-dual active-set solve (same algorithm as
+//              percase.cuh qp_solve_warp / oracle solve_box_qp_exact), compile-time horizon,
+//              Cholesky factor in shared memory, vectors in registers;
+//   plant      lane 0: RK4 / tank map, logs;
+//   lift       CTA-wide: encoder_layers on the 32 new states (tensor path) or 8 RBFs per scenario;
+//   RLS        lanes cooperate: Sherman-Morrison on P and bar_Q, K_A += y v', [A B] = K_A P,
+//              C = bar_X bar_Q (duffing.py:927-953), formula order of the reference.
+//
+// Shapes outside this kernel's specialisation (Tank: nz = 10 + du augmentation, N = 20; N = 50)
+// run on the generic three-kernel path of closed_loop.cu.
+#include "encoder.cuh"
+#include "loopbody.cuh"
+
+namespace kmpc {
+
+constexpr int FG = 8;            // lanes per scenario
+constexpr int FNZ = 8;           // lifted dimension
+constexpr int FN = 10;           // horizon
+constexpr int FNV = FNZ + 1;
+constexpr int kScr = 184;        // scratch doubles per scenario (== 8 mod 16: the two scenarios of a
+                                 // half-warp land on disjoint banks)
+constexpr int kRedPitch = 9;     // pitch of the 8 x 8 reduction buffer (conflict-free column reads)
+// scratch layout during the QP build and the RLS
+constexpr int oRED = 0;          // [8][kRedPitch] cross-lane reduction buffer
+constexpr int oEX = 72;          // 40 doubles: vector exchange (Krylov pairs / g,e / RLS gathers)
+constexpr int oHF = 112;         // 72 doubles: H packed lower triangle (55), f (10), pad
+// scratch layout during the QP solve (aliases RED/EX; HF stays live)
+constexpr int oL = 0;            // 60: strictly-lower factor + forward-substituted rhs, column major
+constexpr int oXS = 60;          // 10: current iterate x
+constexpr int oGS = 70;          // 10: gradient 2 H x + f
+constexpr int kIn0 = 4 * kActStride;   // layer-0 input block (k-major, 4 rows)
+constexpr int kZbuf = kTileS * FNZ;    // lift outputs of the tile
+
+// The identity-output build emits the 55 + 10 reduced values diagonal by diagonal (running sums
+// along a diagonal); this table maps emission number -> position in HF (packed lower triangle
+// tri(a, b) for H, 55 + a for f, identity for the 7 padding slots).
+__constant__ unsigned char c_hf_tab[72] = {
+    54, 44, 35, 27, 20, 14, 9, 5, 2, 0, 53, 43, 34, 26, 19, 13, 8, 4, 1, 52, 42, 33, 25, 18, 12, 7, 3, 51,
+    41, 32, 24, 17, 11, 6, 50, 40, 31, 23, 16, 10, 49, 39, 30, 22, 15, 48, 38, 29, 21, 47, 37, 28, 46, 36,
+    45, 55, 56, 57, 58, 59, 60, 61, 62, 63, 64, 65, 66, 67, 68, 69, 70, 71};
+
+// first element of column j of the factor: rows j+1 .. 10 (row 10 = the right-hand side carried
+// through the elimination), padded to an even length
+__host__ __device__ constexpr int lcol(int j) {
+  int off = 0;
+  for (int k = 0; k < j; ++k) off += ((FN - k) + 1) & ~1;
+  return off;
+}
+
+struct FusedSmem {  // offsets in doubles from the start of dynamic shared memory
+  int scratch, zbuf, in0, wsm, bars, total_bytes;
+};
+inline FusedSmem fused_smem_layout(const EncParams* p) {
+  FusedSmem L;
+  const int act = p ? p->actw * kActStride : 0;
+  const int scr = kTileS * kScr;
+  L.scratch = 0;
+  L.zbuf = (act > scr ? act : scr);
+  L.in0 = L.zbuf + kZbuf;
+  L.wsm = L.in0 + kIn0;
+  L.wsm = (L.wsm + 1) & ~1;
+  L.bars = L.wsm + (p ? p->total_w : 0);
+  L.bars = (L.bars + 1) & ~1;
+  L.total_bytes = (L.bars + KMPC_MAX_LAYERS) * 8;
+  return L;
+}
+
+// sum over the 8 lanes of a scenario of value number `l`: lane l of every group receives the
+// reduced value whose partials the lanes passed in ch[l].  Partials are added in lane order.
+__device__ __forceinline__ double chunk_reduce(double* red, int l, const double (&ch)[8]) {
+#pragma unroll
+  for (int v = 0; v < 8; ++v) red[v * kRedPitch + l] = ch[v];
+  __syncwarp();
+  const double* r = red + l * kRedPitch;
+  const double s = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  __syncwarp();
+  return s;
+}
+
+// every lane of the scenario receives all 8 lane values (in lane order) through `ex`
+__device__ __forceinline__ void group_gather(double* ex, int l, double mine, double (&all)[8]) {
+  ex[l] = mine;
+  __syncwarp();
+  const double2* e2 = reinterpret_cast<const double2*>(ex);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double2 t = e2[j];
+    all[2 * j] = t.x;
+    all[2 * j + 1] = t.y;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- cooperative exact box-QP ---
+// min x'Hx + f'x, lo <= x <= hi for one scenario, executed by its 8 lanes; the 4 scenarios of a
+// warp run in lock step (every loop is warp-uniform; a scenario that has converged keeps executing
+// with its state frozen).  Same algorithm as percase.cuh qp_solve_warp / oracle
+// solve_box_qp_exact (primal-dual active-set sweeps, then the monotone primal method), started
+// from a warm working set.
+//   factor_solve: right-looking Cholesky of the free block of 2H.  Lane i owns row i, lanes 0..2
+//   also own rows 8, 9 and the right-hand side (row 10), so the forward substitution comes for
+//   free; every lane keeps a replicated copy of the running diagonal, hence of the pivots: ONE
+//   __syncwarp per column (the column is the exchange buffer).  The back substitution is done
+//   redundantly by every lane, which leaves the step p replicated in registers.
+struct QpCoop {
+  const double* HF;   // packed lower H (55) | f (10)
+  double* sc;         // Lc (60) | xs (10) | gs (10)
+  int l;              // lane within the scenario
+  int status;
+  int iters;          // active-set iterations of the last run()
+  unsigned wlo, whi;  // working set: bit i set = variable i at its lower / upper bound
+
+  // p <- (2H)_FF^-1 rhs_F (0 on masked variables), rhs = -g on free variables; replicated result
+  __device__ __forceinline__ int factor_solve(unsigned masked, double (&p)[FN]) {
+    double* Lc = sc;
+    const double* gs = sc + oGS;
+    const int r0 = l, r1 = l + 8;            // rows of this lane (r1 valid for l < 3; r1 == 10: rhs)
+    const bool has1 = l < 3;
+    const bool m0 = (masked >> r0) & 1u, m1 = (r1 < FN) && ((masked >> r1) & 1u);
+    const int b0 = (r0 * (r0 + 1)) >> 1, b1 = (r1 < FN) ? (r1 * (r1 + 1)) >> 1 : 0;
+    double a0[FNZ], a1[FN], dg[FN], invd[FN];
+    int st = 0;
+#pragma unroll
+    for (int k = 0; k < FN; ++k) {
+      const bool mk = (masked >> k) & 1u;
+      if (k < FNZ) a0[k] = (m0 || mk || k > r0) ? 0.0 : 2.0 * HF[b0 + (k <= r0 ? k : 0)];
+      double v1;
+      if (r1 < FN) v1 = (m1 || mk || k > r1) ? 0.0 : 2.0 * HF[b1 + (k <= r1 ? k : 0)];
+      else v1 = mk ? 0.0 : -gs[k];           // right-hand side row
+      a1[k] = has1 ? v1 : 0.0;
+      dg[k] = mk ? 1.0 : 2.0 * HF[tri(k, k)];
+    }
+#pragma unroll
+    for (int j = 0; j < FN; ++j) {
+      double d = dg[j];
+      if (!(d > 0.0)) {
+        st |= KMPC_STATUS_PIVOT;
+        d = 1e-300;
+      }
+      const double inv = rsqrt(d);
+      invd[j] = inv;
+      // column j: L[r][j] = a[r][j] / L[j][j] for the rows below the diagonal (and y_j in row 10)
+      double c0 = 0.0;
+      if (j < FNZ - 1) {
+        c0 = a0[j] * inv;
+        if (r0 > j) Lc[lcol(j) + r0 - j - 1] = c0;
+      }
+      const double c1 = a1[j] * inv;
+      if (has1 && r1 > j) Lc[lcol(j) + r1 - j - 1] = c1;
+      __syncwarp();
+      double col[FN + 1];
+#pragma unroll
+      for (int k = j + 1; k <= FN; ++k) col[k] = Lc[lcol(j) + k - j - 1];
+#pragma unroll
+      for (int k = j + 1; k < FN; ++k) {
+        if (k < FNZ) a0[k] = fma(-c0, col[k], a0[k]);
+        a1[k] = fma(-c1, col[k], a1[k]);
+        dg[k] = fma(-col[k], col[k], dg[k]);
+      }
+      p[j] = col[FN];   // y_j
+    }
+    // back substitution L' x = y, every lane redundantly
+#pragma unroll
+    for (int jj = 0; jj < FN; ++jj) {
+      const int j = FN - 1 - jj;
+      double s0 = p[j], s1 = 0.0;
+#pragma unroll
+      for (int r = j + 1; r < FN; ++r) {
+        if ((r - j) & 1) s0 = fma(-Lc[lcol(j) + r - j - 1], p[r], s0);
+        else s1 = fma(-Lc[lcol(j) + r - j - 1], p[r], s1);
+      }
+      p[j] = (s0 + s1) * invd[j];
+    }
+    __syncwarp();   // Lc is rewritten by the next factorisation
+    return st;
+  }
+
+  // gs = 2 H xs + f: lane i computes rows i (and i + 8), then the group exchanges through gs
+  __device__ __forceinline__ void gradient() {
+    const double* xs = sc + oXS;
+    double* gs = sc + oGS;
+    double xv[FN];
+#pragma unroll
+    for (int j = 0; j < FN; ++j) xv[j] = xs[j];
+#pragma unroll
+    for (int slot = 0; slot < 2; ++slot) {
+      const int r = l + 8 * slot;
+      if (r < FN) {
+        const int br = (r * (r + 1)) >> 1;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < FN; j += 2) {
+          s0 = fma(HF[j <= r ? br + j : tri(j, 0) + r], xv[j], s0);
+          s1 = fma(HF[j + 1 <= r ? br + j + 1 : tri(j + 1, 0) + r], xv[j + 1], s1);
+        }
+        gs[r] = fma(2.0, s0 + s1, HF[55 + r]);
+      }
+    }
+    __syncwarp();
+  }
+
+  // Returns the first move; leaves the final working set in (wlo, whi).  Every lane of the
+  // scenario returns the same value.
+  __device__ __forceinline__ double run(double lo, double hi, int max_iter, double tol) {
+    status = 0;
+    iters = 0;
+    double* xs = sc + oXS;
+    double* gs = sc + oGS;
+    double fmaxabs = 0.0;
+#pragma unroll
+    for (int i = 0; i < FN; ++i) fmaxabs = fmax(fmaxabs, fabs(HF[55 + i]));
+    const double mtol = tol * fmax(1.0, fmaxabs);
+    const double x0 = fmin(fmax(0.0, lo), hi);
+    const bool cold = (wlo | whi) == 0u && x0 == 0.0;
+    if (l == 0) {
+#pragma unroll
+      for (int i = 0; i < FN; ++i) {
+        xs[i] = ((wlo >> i) & 1u) ? lo : (((whi >> i) & 1u) ? hi : x0);
+        gs[i] = HF[55 + i];    // gradient at x = 0 (cold start)
+      }
+    }
+    __syncwarp();
+    // warm start: gradient at the start point (for a cold scenario x = 0 and this reproduces g = f)
+    if (__any_sync(0xffffffffu, !cold)) gradient();
+    bool done = false;
+    for (int it = 0; it < max_iter; ++it) {
+      if (!__any_sync(0xffffffffu, !done)) break;
+      if (!done) ++iters;
+      const bool pdas = it < kPdasIters;
+      const unsigned masked = wlo | whi;
+      double p[FN];
+      const int st = factor_solve(masked, p);
+      if (!done) status |= st;
+      double alpha = 1.0;
+      int block = -1;
+      if (!pdas) {  // ratio test; lowest index wins ties
+#pragma unroll
+        for (int i = 0; i < FN; ++i) {
+          if (!((masked >> i) & 1u)) {
+            const double pi = p[i], xi = xs[i];
+            double a = 2.0;
+            if (pi > 0.0 && xi + pi > hi) a = (hi - xi) / pi;
+            else if (pi < 0.0 && xi + pi < lo) a = (lo - xi) / pi;
+            if (a < alpha) {
+              alpha = a;
+              block = i;
+            }
+          }
+        }
+      }
+      unsigned nlo = wlo, nhi = whi;
+      double xn[FN];
+#pragma unroll
+      for (int i = 0; i < FN; ++i) {
+        double xi = fma(alpha, p[i], xs[i]);
+        if (i == block) {
+          if (p[i] > 0.0) {
+            xi = hi;
+            nhi |= 1u << i;
+          } else {
+            xi = lo;
+            nlo |= 1u << i;
+          }
+        }
+        xn[i] = xi;
+      }
+      __syncwarp();   // every lane has read xs
+      if (l == 0 && !done) {
+#pragma unroll
+        for (int i = 0; i < FN; ++i) xs[i] = xn[i];
+      }
+      __syncwarp();
+      bool finished = false;
+      if (pdas) {
+        // multipliers (gradient at the unclipped face minimiser) are needed only when something
+        // is bound; the free components of the gradient vanish there
+        if (__any_sync(0xffffffffu, !done && masked != 0u)) gradient();
+        bool changed = false, clipped = false;
+#pragma unroll
+        for (int i = 0; i < FN; ++i) {
+          const unsigned bit = 1u << i;
+          if (masked & bit) {       // release every bound whose multiplier has the wrong sign
+            const double lamb = (nlo & bit) ? gs[i] : -gs[i];
+            if (lamb < -mtol) {
+              nlo &= ~bit;
+              nhi &= ~bit;
+              changed = true;
+            }
+          } else if (xn[i] < lo) {  // clip every violated bound into the working set
+            xn[i] = lo;
+            nlo |= bit;
+            clipped = true;
+          } else if (xn[i] > hi) {
+            xn[i] = hi;
+            nhi |= bit;
+            clipped = true;
+          }
+        }
+        finished = !changed && !clipped;
+        __syncwarp();
+        if (l == 0 && !done && clipped) {
+#pragma unroll
+          for (int i = 0; i < FN; ++i) xs[i] = xn[i];
+        }
+        __syncwarp();
+        // next iteration starts from the gradient at the clipped point
+        if (__any_sync(0xffffffffu, !done && !finished && (clipped || masked == 0u))) gradient();
+      } else {
+        gradient();
+        double worst = INFINITY;
+        int widx = -1;
+#pragma unroll
+        for (int i = 0; i < FN; ++i) {
+          const unsigned bit = 1u << i;
+          if ((nlo | nhi) & bit) {
+            const double lamb = (nlo & bit) ? gs[i] : -gs[i];
+            if (lamb < worst) {
+              worst = lamb;
+              widx = i;
+            }
+          }
+        }
+        if (block < 0) {
+          if (widx < 0 || worst >= -mtol) {
+            finished = true;
+          } else {
+            nlo &= ~(1u << widx);
+            nhi &= ~(1u << widx);
+          }
+        }
+      }
+      if (!done) {   // converged scenarios keep their state frozen
+        wlo = nlo;
+        whi = nhi;
+        done = finished;
+      }
+    }
+    if (!done) status |= KMPC_STATUS_MAXITER;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < FN; ++i) bad |= !isfinite(xs[i]);
+    if (bad) {
+      status |= KMPC_STATUS_NONFINITE;
+      wlo = whi = 0u;
+    }
+    const double u0 = xs[0];
+    __syncwarp();
+    return u0;
+  }
+};
+
+// ---------------------------------------------------------------- the kernel -----------------
+// OUT: KMPC_OUT_IDENTITY (y = z, vanderpol.py) or KMPC_OUT_C (y = C z, duffing.py);
+// UPDATE: online RLS; MLP: theta_E lift (else thin-plate RBF); TIMED: per-phase clock64 sums.
+struct FusedArgs {
+  LoopDev d;
+  EncParams p;        // MLP only
+  FusedSmem sm;
+  int64_t step0;      // closed-loop index of the first step of this launch
+  int T;              // steps in this launch
+  int first;          // 1: the first step restarts the RLS state (P = p0 I, bar_Q = q0 I)
+  int64_t num_tiles;
+  long long* timing;  // TIMED: [gridDim.x][4] cycles in QP+plant, lift, RLS, total
+  int dbg_skip;       // profiling aid (KMPC_FUSED_SKIP): bit 0 skip QP, bit 1 skip lift, bit 2 skip RLS,
+                      // bit 3 log the active-set iteration count in log_u instead of u
+};
+
+template <int OUT, bool UPDATE, bool MLP, bool TIMED>
+__global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid_constant__ FusedArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const kmpc_loop_config& c = a.d.c;
+  const kmpc_loop_buffers& b = a.d.b;
+  double* zbuf = smem + a.sm.zbuf;
+  double* in0 = smem + a.sm.in0;
+  double* wsm = smem + a.sm.wsm;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.sm.bars);
+  const int tid = threadIdx.x;
+  const int sc = tid >> 3, l = tid & 7;
+  double* scr = smem + a.sm.scratch + sc * kScr;
+  double* red = scr + oRED;
+  double* ex = scr + oEX;
+  double* HF = scr + oHF;
+  if (MLP) {
+    if (tid == 0) encoder_weights_init_barriers(a.p, bars);
+    __syncthreads();
+    if (tid == 0) encoder_weights_issue(a.p, wsm, bars);
+  }
+  const bool upc = (c.rls_flags & KMPC_RLS_UPDATE_C) != 0;
+  const double lam = c.lambda;
+  long long tq = 0, tl = 0, tr = 0, t_begin = 0;
+  if (TIMED) t_begin = clock64();
+
+  for (int64_t tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    int64_t s = tile * kTileS + sc;
+    const bool valid = s < c.S;
+    if (!valid) s = c.S - 1;
+    const int64_t sm = c.shared_model ? 0 : s;
+    // ---- state -> registers (lane l = row l) ----
+    // A, B: frozen model -> registers for the whole launch; online update -> they are produced by
+    // the RLS at the end of a step and consumed by the Krylov chains at the start of the next one,
+    // so they wait in the (then idle) HF part of the scratch, transposed (lane-contiguous)
+    double Ar[FNZ], Bl, Cc0 = 0.0, Cc1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < FNZ; ++j) Ar[j] = b.A[sm * 64 + l * 8 + j];
+    Bl = b.B[sm * 8 + l];
+    if (UPDATE) {
+#pragma unroll
+      for (int j = 0; j < FNZ; ++j) HF[j * 8 + l] = Ar[j];
+      HF[64 + l] = Bl;
+    }
+    if (OUT == KMPC_OUT_C || UPDATE) {
+      Cc0 = b.C[sm * 16 + l];
+      Cc1 = b.C[sm * 16 + 8 + l];
+    }
+    double zl = b.z[s * 8 + l];
+    double x1 = b.x[s * 2], x2 = b.x[s * 2 + 1];
+    double uprev = b.u_prev[s];
+    double rl = 0.0, r0 = 0.0, r1 = 0.0;
+    if (OUT == KMPC_OUT_IDENTITY) {
+      rl = b.r[s * 8 + l];
+    } else {
+      r0 = b.r[s * 2];
+      r1 = b.r[s * 2 + 1];
+    }
+    double KAr[FNV], Pr[FNV], P8l = 0.0, P88 = 0.0, Qr[FNZ], Xc0 = 0.0, Xc1 = 0.0;
+    if (UPDATE) {
+      if (a.first) {  // duffing.py:927-930, 943-946
+#pragma unroll
+        for (int j = 0; j < FNV; ++j) {
+          KAr[j] = 0.0;
+          Pr[j] = (j == l) ? c.p0 : 0.0;
+        }
+        P88 = c.p0;
+#pragma unroll
+        for (int j = 0; j < FNZ; ++j) Qr[j] = (j == l) ? c.q0 : 0.0;
+      } else {
+#pragma unroll
+        for (int j = 0; j < FNV; ++j) {
+          KAr[j] = b.KA[s * 72 + l * 9 + j];
+          Pr[j] = b.P[s * 81 + l * 9 + j];
+        }
+        P8l = b.P[s * 81 + 72 + l];
+        P88 = b.P[s * 81 + 80];
+        if (upc) {
+#pragma unroll
+          for (int j = 0; j < FNZ; ++j) Qr[j] = b.barQ[s * 64 + l * 8 + j];
+          Xc0 = b.barX[s * 16 + l];
+          Xc1 = b.barX[s * 16 + 8 + l];
+        } else {
+#pragma unroll
+          for (int j = 0; j < FNZ; ++j) Qr[j] = 0.0;
+        }
+      }
+    }
+    int status = 0;
+    unsigned wlo = 0u, whi = 0u;   // optimal working set of the previous step (lane 0)
+    if (a.d.wset) {
+      const uint2 w2 = reinterpret_cast<const uint2*>(a.d.wset)[s];
+      wlo = w2.x;
+      whi = w2.y;
+    }
+
+    for (int t = 0; t < a.T; ++t) {
+      const int64_t step = a.step0 + t;
+      long long c0 = 0;
+      if (TIMED) c0 = clock64();
+      double x1n = x1, x2n = x2, unew = uprev;
+      if (!(a.dbg_skip & 1)) {
+      // ================= QP build: Krylov chains =================
+      double VZ[FN], VB[FN];
+      if (UPDATE) {
+#pragma unroll
+        for (int j = 0; j < FNZ; ++j) Ar[j] = HF[j * 8 + l];
+        Bl = HF[64 + l];
+      }
+      VB[0] = Bl;
+      ex[l] = zl;
+      ex[8 + l] = Bl;
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < FN; ++k) {
+        const double2* src = reinterpret_cast<const double2*>(ex + (k & 1) * 16);
+        double zv[8], bv[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 tz = src[j];
+          zv[2 * j] = tz.x;
+          zv[2 * j + 1] = tz.y;
+        }
+        double sz = 0.0;
+#pragma unroll
+        for (int j = 0; j < FNZ; ++j) sz = fma(Ar[j], zv[j], sz);
+        VZ[k] = sz;
+        if (k + 1 < FN) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double2 tb = src[4 + j];
+            bv[2 * j] = tb.x;
+            bv[2 * j + 1] = tb.y;
+          }
+          double sb = 0.0;
+#pragma unroll
+          for (int j = 0; j < FNZ; ++j) sb = fma(Ar[j], bv[j], sb);
+          VB[k + 1] = sb;
+          double* dst = ex + ((k + 1) & 1) * 16;
+          dst[l] = sz;
+          dst[8 + l] = sb;
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+      // ================= QP build: H and f =================
+      if (OUT == KMPC_OUT_IDENTITY) {
+        // g[t] = VB[t], e[t] = VZ[t] - r: lane l holds component l; partial sums over its own
+        // component, reduced over the 8 lanes in chunks of 8 values (emission order = HF order)
+        double ch[8];
+        int n = 0;
+#pragma unroll
+        for (int dd = 0; dd < FN; ++dd) {
+          double run = 0.0;
+#pragma unroll
+          for (int k = 0; k + dd < FN; ++k) {
+            run = fma(VB[k + dd], VB[k], run);
+            ch[n & 7] = c.q * run;
+            ++n;
+            if ((n & 7) == 0) {
+              const double sum = chunk_reduce(red, l, ch);
+              const int idx = n - 8 + l;
+              HF[c_hf_tab[idx]] = sum + (idx < FN ? c.rw : 0.0);
+            }
+          }
+        }
+#pragma unroll
+        for (int aa = 0; aa < FN; ++aa) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int k = aa; k < FN; ++k) sacc = fma(VB[k - aa], VZ[k] - rl, sacc);
+          ch[n & 7] = 2.0 * c.q * sacc;
+          ++n;
+          if ((n & 7) == 0) {
+            const double sum = chunk_reduce(red, l, ch);
+            HF[c_hf_tab[n - 8 + l]] = sum;
+          }
+        }
+        // n == 65: one value left in ch[0]
+#pragma unroll
+        for (int v = 1; v < 8; ++v) ch[v] = 0.0;
+        {
+          const double sum = chunk_reduce(red, l, ch);
+          HF[64 + l] = sum;
+        }
+      } else {
+        // g[t] = C VB[t], e[t] = C VZ[t] - r (ny = 2): 40 values reduced over the lanes into
+        // ex[4 t + {0,1}] = g[t], ex[4 t + {2,3}] = e[t]
+        double ge[5];
+#pragma unroll
+        for (int q5 = 0; q5 < 5; ++q5) {
+          double ch[8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = 2 * q5 + h;
+            ch[4 * h + 0] = Cc0 * VB[k];
+            ch[4 * h + 1] = Cc1 * VB[k];
+            ch[4 * h + 2] = Cc0 * VZ[k];
+            ch[4 * h + 3] = Cc1 * VZ[k];
+          }
+          ge[q5] = chunk_reduce(red, l, ch);
+        }
+        // lane l received value l of every chunk: (l & 3) >= 2 are e entries
+        const double roff = ((l & 3) == 2) ? r0 : (((l & 3) == 3) ? r1 : 0.0);
+#pragma unroll
+        for (int q5 = 0; q5 < 5; ++q5) ex[8 * q5 + l] = ge[q5] - roff;
+        __syncwarp();
+        // diagonals of H: pair-task pt = d and 9 - d (11 dot products); f likewise
+        for (int task = l; task < 10; task += FG) {
+          const bool isf = task >= 5;
+          const int d0 = isf ? task - 5 : task;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            const int dd = half ? (FN - 1 - d0) : d0;
+            if (!isf) {
+              double run = 0.0;
+              for (int k = 0; k + dd < FN; ++k) {
+                const double2 g1 = *reinterpret_cast<const double2*>(ex + 4 * (k + dd));
+                const double2 g0 = *reinterpret_cast<const double2*>(ex + 4 * k);
+                run = fma(g1.x, g0.x, run);
+                run = fma(g1.y, g0.y, run);
+                const int ra = FN - 1 - k;   // H[ra][ra - dd]
+                HF[((ra * (ra + 1)) >> 1) + ra - dd] = c.q * run + (dd == 0 ? c.rw : 0.0);
+              }
+            } else {
+              double sacc = 0.0;  // f[a], a = dd
+              for (int k = dd; k < FN; ++k) {
+                const double2 g0 = *reinterpret_cast<const double2*>(ex + 4 * (k - dd));
+                const double2 e1 = *reinterpret_cast<const double2*>(ex + 4 * k + 2);
+                sacc = fma(g0.x, e1.x, sacc);
+                sacc = fma(g0.y, e1.y, sacc);
+              }
+              HF[55 + dd] = 2.0 * c.q * sacc;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      // ================= QP solve (8 lanes) + plant (lane 0) =================
+      {
+        QpCoop qp;
+        qp.HF = HF;
+        qp.sc = scr + oL;
+        qp.l = l;
+        // warm start: last step's optimal working set, shifted by one move (receding horizon)
+        qp.wlo = (wlo >> 1) | (wlo & (1u << (FN - 1)));
+        qp.whi = (whi >> 1) | (whi & (1u << (FN - 1)));
+        unew = qp.run(c.lb, c.ub, c.max_iter, c.tol);
+        status |= qp.status;
+        wlo = qp.wlo;
+        whi = qp.whi;
+        if (l == 0) {
+          const double* pp = (step < c.first_post_step ? b.params_pre : b.params_post) + s * 5;
+          double prm[5];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) prm[k] = __ldg(pp + k);
+          plant_step_dev(c.plant_kind, c.rk4_variant, c.h, prm, x1, x2, unew, x1n, x2n);
+          if (valid) {
+            const int64_t slot = (step < b.log_capacity) ? step : -1;
+            if (b.log_x && slot >= 0) {
+              b.log_x[(slot * c.S + s) * 2] = x1n;
+              b.log_x[(slot * c.S + s) * 2 + 1] = x2n;
+            }
+            if (b.log_u && slot >= 0) b.log_u[slot * c.S + s] = (a.dbg_skip & 8) ? (double)qp.iters : unew;
+          }
+        }
+      }
+      __syncwarp();
+      x1n = __shfl_sync(0xffffffffu, x1n, 0, FG);
+      x2n = __shfl_sync(0xffffffffu, x2n, 0, FG);
+      unew = __shfl_sync(0xffffffffu, unew, 0, FG);
+      }
+      // ================= lift(x+) =================
+      double yl;
+      if (MLP) {
+        if (l < 4) in0[l * kActStride + sc] = (l == 0) ? x1n : ((l == 1) ? x2n : 0.0);
+        __syncthreads();
+        if (TIMED) tq += clock64() - c0, c0 = clock64();
+        if (!(a.dbg_skip & 2))
+          encoder_layers(a.p, in0, smem, wsm, bars, [&](int r, int col, double v) { zbuf[r * FNZ + col] = v; });
+        yl = zbuf[sc * FNZ + l];
+        if (c.lift_mode != KMPC_LIFT_RAW) yl -= a.p.z0[l];
+        if (TIMED) tl += clock64() - c0, c0 = clock64();
+      } else {
+        if (TIMED) tq += clock64() - c0, c0 = clock64();
+        const double xx[2] = {x1n, x2n};
+        yl = rbf_thinplate(xx, b.cx + l * 2, 2, c.lift_mode);
+        if (TIMED) tl += clock64() - c0, c0 = clock64();
+      }
+      // ================= RLS (duffing.py:927-953, 965-984) =================
+      if (UPDATE && !(a.dbg_skip & 4)) {
+        double zv[8];
+        group_gather(ex, l, zl, zv);
+        const double u = unew;
+        // w = P v (rows l and 8), rrow = v'P
+        double w = 0.0;
+#pragma unroll
+        for (int j = 0; j < FNZ; ++j) w = fma(Pr[j], zv[j], w);
+        w = fma(Pr[8], u, w);
+        double p8v[8];
+        group_gather(ex + 8, l, P8l, p8v);
+        double w8 = 0.0;
+#pragma unroll
+        for (int j = 0; j < FNZ; ++j) w8 = fma(p8v[j], zv[j], w8);
+        w8 = fma(P88, u, w8);
+        double ch[8];
+#pragma unroll
+        for (int j = 0; j < FNZ; ++j) ch[j] = zl * Pr[j];
+        double rr = chunk_reduce(red, l, ch);
+        rr = fma(u, P8l, rr);                    // rrow[l]
+        double c8[8];
+        group_gather(ex + 16, l, zl * Pr[8], c8);
+        double rr8 = c8[0];
+#pragma unroll
+        for (int j = 1; j < FNZ; ++j) rr8 += c8[j];
+        rr8 = fma(u, P88, rr8);                  // rrow[8]
+        double rv[8];
+        group_gather(ex + 24, l, rr, rv);
+        double vPv = 0.0;                        // (v'P) v, duffing.py:934
+#pragma unroll
+        for (int j = 0; j < FNZ; ++j) vPv = fma(rv[j], zv[j], vPv);
+        vPv = fma(rr8, u, vPv);
+        const double denom = lam + vPv;
+        if (lam == 1.0) {  // x / 1 == x exactly; one reciprocal instead of eleven divisions
+          const double wd = w / denom, w8d = w8 / denom;
+#pragma unroll
+          for (int j = 0; j < FNZ; ++j) Pr[j] = fma(-wd, rv[j], Pr[j]);
+          Pr[8] = fma(-wd, rr8, Pr[8]);
+          P8l = fma(-w8d, rr, P8l);
+          P88 = fma(-w8d, rr8, P88);
+        } else {           // Koopman_update.m:270 forgetting factor
+#pragma unroll
+          for (int j = 0; j < FNZ; ++j) Pr[j] = Pr[j] / lam - (w * rv[j]) / lam / denom;
+          Pr[8] = Pr[8] / lam - (w * rr8) / lam / denom;
+          P8l = P8l / lam - (w8 * rr) / lam / denom;
+          P88 = P88 / lam - (w8 * rr8) / lam / denom;
+        }
+#pragma unroll
+        for (int j = 0; j < FNZ; ++j) KAr[j] = fma(yl, zv[j], KAr[j]);
+        KAr[8] = fma(yl, u, KAr[8]);
+        // [A B] = K_A P: all-gather the new P through the scratch (81 doubles)
+        double* Pm = scr;
+#pragma unroll
+        for (int j = 0; j < FNV; ++j) Pm[l * 9 + j] = Pr[j];
+        Pm[72 + l] = P8l;
+        if (l == 0) Pm[80] = P88;
+        __syncwarp();
+#pragma unroll 1
+        for (int j = 0; j < FNV; ++j) {   // column j of [A B]; j == 8 is B (HF[64 + l])
+          double sacc = 0.0;
+#pragma unroll
+          for (int k = 0; k < FNV; ++k) sacc = fma(KAr[k], Pm[k * 9 + j], sacc);
+          HF[j * 8 + l] = sacc;
+        }
+        __syncwarp();
+        if (upc) {
+          double wq = 0.0;
+#pragma unroll
+          for (int j = 0; j < FNZ; ++j) wq = fma(Qr[j], zv[j], wq);
+#pragma unroll
+          for (int j = 0; j < FNZ; ++j) ch[j] = zl * Qr[j];
+          const double rq = chunk_reduce(red, l, ch);
+          double rqv[8];
+          group_gather(ex, l, rq, rqv);
+          double zQz = 0.0;
+#pragma unroll
+          for (int j = 0; j < FNZ; ++j) zQz = fma(rqv[j], zv[j], zQz);
+          const double dq = 1.0 + zQz;
+          const double wqd = wq / dq;
+#pragma unroll
+          for (int j = 0; j < FNZ; ++j) Qr[j] = fma(-wqd, rqv[j], Qr[j]);
+          const bool skipx = (t == 0 && a.first && c.skip_first_barx);  // Tank_System.m:252-254
+          if (!skipx) {
+            const double xc0 = c.c_pairs_next ? x1n : x1, xc1 = c.c_pairs_next ? x2n : x2;
+            Xc0 = fma(xc0, zl, Xc0);
+            Xc1 = fma(xc1, zl, Xc1);
+          }
+#pragma unroll
+          for (int j = 0; j < FNZ; ++j) ch[j] = Xc0 * Qr[j];
+          Cc0 = chunk_reduce(red, l, ch);
+#pragma unroll
+          for (int j = 0; j < FNZ; ++j) ch[j] = Xc1 * Qr[j];
+          Cc1 = chunk_reduce(red, l, ch);
+        }
+      }
+      zl = yl;
+      x1 = x1n;
+      x2 = x2n;
+      uprev = unew;
+      if (TIMED) tr += clock64() - c0;
+    }
+
+    // ---- registers -> state ----
+    if (valid) {
+      b.z[s * 8 + l] = zl;
+      if (l == 0) {
+        b.x[s * 2] = x1;
+        b.x[s * 2 + 1] = x2;
+        b.u_prev[s] = uprev;
+        if (b.status && status) b.status[s] |= status;
+        if (a.d.wset) reinterpret_cast<uint2*>(a.d.wset)[s] = make_uint2(wlo, whi);
+      }
+      if (UPDATE && a.T > 0) {
+#pragma unroll
+        for (int j = 0; j < FNZ; ++j) b.A[s * 64 + l * 8 + j] = HF[j * 8 + l];
+        b.B[s * 8 + l] = HF[64 + l];
+#pragma unroll
+        for (int j = 0; j < FNV; ++j) {
+          b.KA[s * 72 + l * 9 + j] = KAr[j];
+          b.P[s * 81 + l * 9 + j] = Pr[j];
+        }
+        b.P[s * 81 + 72 + l] = P8l;
+        if (l == 0) b.P[s * 81 + 80] = P88;
+        if (upc) {
+          b.C[s * 16 + l] = Cc0;
+          b.C[s * 16 + 8 + l] = Cc1;
+#pragma unroll
+          for (int j = 0; j < FNZ; ++j) b.barQ[s * 64 + l * 8 + j] = Qr[j];
+          b.barX[s * 16 + l] = Xc0;
+          b.barX[s * 16 + 8 + l] = Xc1;
+        }
+      }
+    }
+    __syncthreads();  // the next tile reuses scratch / zbuf
+  }
+  if (TIMED && tid == 0) {
+    a.timing[blockIdx.x * 4 + 0] = tq;
+    a.timing[blockIdx.x * 4 + 1] = tl;
+    a.timing[blockIdx.x * 4 + 2] = tr;
+    a.timing[blockIdx.x * 4 + 3] = clock64() - t_begin;
+  }
+}
+
+typedef void (*FusedKernel)(const FusedArgs);
+
+template <bool TIMED>
+static FusedKernel pick_fused(int out_mode, bool update, bool mlp) {
+  if (out_mode == KMPC_OUT_IDENTITY) {
+    if (update) return mlp ? fused_loop_kernel<KMPC_OUT_IDENTITY, true, true, TIMED>
+                           : fused_loop_kernel<KMPC_OUT_IDENTITY, true, false, TIMED>;
+    return mlp ? fused_loop_kernel<KMPC_OUT_IDENTITY, false, true, TIMED>
+               : fused_loop_kernel<KMPC_OUT_IDENTITY, false, false, TIMED>;
+  }
+  if (update) return mlp ? fused_loop_kernel<KMPC_OUT_C, true, true, TIMED>
+                         : fused_loop_kernel<KMPC_OUT_C, true, false, TIMED>;
+  return mlp ? fused_loop_kernel<KMPC_OUT_C, false, true, TIMED> : fused_loop_kernel<KMPC_OUT_C, false, false, TIMED>;
+}
+
+// Can the fused kernel run this loop?  (KMPC_FUSED=0 forces the generic three-kernel path.)
+bool fused_eligible(const kmpc_loop_config& c, const kmpc_encoder* enc) {
+  const char* e = getenv("KMPC_FUSED");  // read per context so tests can compare both paths
+  if (e && e[0] == '0') return false;
+  if (c.nz != FNZ || c.N != FN || c.n != 2 || c.du_aug) return false;
+  if (c.out_mode != KMPC_OUT_IDENTITY && c.out_mode != KMPC_OUT_C) return false;
+  if (c.update && !(c.rls_flags & KMPC_RLS_UPDATE_C) && c.out_mode == KMPC_OUT_C) {
+    // C is then a frozen input: fine, it is simply never rewritten
+  }
+  if (c.lift_kind == KMPC_LIFTKIND_MLP) {
+    if (!enc || enc->smem_bytes <= 0) return false;
+    if (c.lift_mode == KMPC_LIFT_STACK) return false;
+    if (enc->p.dims[0] != 2 || enc->p.dims[enc->p.n_layers] != FNZ) return false;
+    const FusedSmem L = fused_smem_layout(&enc->p);
+    if (L.total_bytes > enc->max_smem_optin) return false;
+  } else if (c.lift_kind != KMPC_LIFTKIND_RBF) {
+    return false;
+  }
+  return true;
+}
+
+// Launch T steps.  `timing` (nullable, device, [grid][4] long long) selects the TIMED build.
+int fused_launch(const LoopDev& d, const kmpc_encoder* enc, int64_t step0, int T, int first,
+                 long long* timing, int* grid_out, cudaStream_t st) {
+  const kmpc_loop_config& c = d.c;
+  const bool mlp = c.lift_kind == KMPC_LIFTKIND_MLP;
+  FusedArgs a;
+  a.d = d;
+  if (mlp) a.p = enc->p;
+  else memset(&a.p, 0, sizeof(a.p));
+  a.sm = fused_smem_layout(mlp ? &enc->p : nullptr);
+  a.step0 = step0;
+  a.T = T;
+  a.first = first;
+  a.num_tiles = (c.S + kTileS - 1) / kTileS;
+  a.timing = timing;
+  {
+    const char* e = getenv("KMPC_FUSED_SKIP");
+    a.dbg_skip = e ? atoi(e) : 0;
+  }
+  int dev = 0, sms = 148;
+  KMPC_CUDA(cudaGetDevice(&dev));
+  KMPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t cap = mlp ? sms : (int64_t)sms * 4;
+  const unsigned grid = (unsigned)(a.num_tiles < cap ? a.num_tiles : cap);
+  FusedKernel k = timing ? pick_fused<true>(c.out_mode, c.update != 0, mlp)
+                         : pick_fused<false>(c.out_mode, c.update != 0, mlp);
+  KMPC_CUDA(ensure_smem(k, a.sm.total_bytes));
+  k<<<grid, kMmaThreads, a.sm.total_bytes, st>>>(a);
+  KMPC_AFTER_LAUNCH();
+  if (grid_out) *grid_out = (int)grid;
+  return KMPC_OK;
+}
+
+}  // namespace kmpc

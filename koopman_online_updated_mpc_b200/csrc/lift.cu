@@ -18,67 +18,12 @@
 // weight (== 4 mod 16) arrays make every fragment load bank-conflict free.
 // encoder_kernel (fallback for nets that do not fit 227 KB): CUDA-core 4x4 register tiles,
 // weights read from global/L2.
-#include <vector>
-
-#include "common.cuh"
+#include "encoder.cuh"
 
 namespace kmpc {
 
-constexpr int kTileS = 32;         // scenarios per CTA
 constexpr int kEncWarps = 7;       // 7 warps x 4 column groups x 4 outputs = 112 outputs per pass
 constexpr int kEncThreads = kEncWarps * 32;
-
-struct EncParams {
-  int n_layers;
-  int dims[KMPC_MAX_LAYERS + 1];
-  int pad[KMPC_MAX_LAYERS + 1];
-  const double* wt[KMPC_MAX_LAYERS];
-  const double* b[KMPC_MAX_LAYERS];
-  const double* z0;
-  const double* packed;            // [W1t | b1 | W2t | b2 | ...] (same layout as the smem copy)
-  int woff[KMPC_MAX_LAYERS];       // offset (doubles) of layer l's W block inside `packed`
-  int wlen[KMPC_MAX_LAYERS];       // doubles of layer l's W + bias block
-  int total_w;                     // doubles in `packed`
-  int actw;                        // activation buffer width (max padded layer width)
-  int wstride[KMPC_MAX_LAYERS];    // row stride (doubles) of layer l's W^T block, == 4 (mod 16)
-  int inpad[KMPC_MAX_LAYERS];      // rows of layer l's W^T block (in rounded up to 4, zero rows)
-};
-
-// ---- TMA bulk-copy / mbarrier helpers (PTX; SASS: UBLKCP, SYNCS) --------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
 
 // One layer of the 4x4 register-tiled GEMM for this thread: acc = bias + act_in^T W.
 // WT_LD: functor-free: weights read with plain loads from `wt` (shared or global pointer).
@@ -158,20 +103,8 @@ __device__ __forceinline__ void enc_store_tile(const double (&acc)[4][4], bool l
   }
 }
 
-constexpr int kMmaWarps = 8;
-constexpr int kMmaThreads = kMmaWarps * 32;
-constexpr int kActStride = 36;  // doubles per activation row k: 32 scenarios + 4 pad (== 4 mod 16)
-
-__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
 // Persistent CTAs, weights resident in shared memory (loaded once by TMA bulk copies), layer GEMMs
-// on the fp64 tensor path.  Warp w owns rows 16*(w&1)..+15 (two m-tiles) and the n-tiles
-// {w>>1, (w>>1)+4, ...} of every layer; activations live in ONE k-major buffer that is rewritten
-// in place between two barriers.
+// on the fp64 tensor path (encoder.cuh: encoder_layers).
 __global__ void __launch_bounds__(kMmaThreads, 1)
 encoder_mma_kernel(EncParams p, const double* __restrict__ x, double* __restrict__ z, int64_t S,
                    int lift_mode, int out_dim, int64_t num_tiles) {
@@ -179,31 +112,15 @@ encoder_mma_kernel(EncParams p, const double* __restrict__ x, double* __restrict
   double* act = smem;
   double* wsm = smem + p.actw * kActStride;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + p.total_w);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    for (int l = 0; l < p.n_layers; ++l) mbar_init(&bars[l], 1);
-    mbar_fence_init();
-  }
+  const int tid = threadIdx.x;
+  if (tid == 0) encoder_weights_init_barriers(p, bars);
   __syncthreads();
-  if (tid == 0) {
-    for (int l = 0; l < p.n_layers; ++l) {
-      const uint32_t bytes = (uint32_t)p.wlen[l] * 8u;
-      mbar_expect_tx(&bars[l], bytes);
-      for (uint32_t o = 0; o < bytes; o += 32768u) {
-        const uint32_t sz = (bytes - o < 32768u) ? (bytes - o) : 32768u;
-        bulk_copy_g2s(reinterpret_cast<char*>(wsm + p.woff[l]) + o,
-                      reinterpret_cast<const char*>(p.packed + p.woff[l]) + o, sz, &bars[l]);
-      }
-    }
-  }
+  if (tid == 0) encoder_weights_issue(p, wsm, bars);
   // the weight copies above do not depend on the previous kernel: only now wait for it (PDL)
   pdl_wait();
   pdl_launch_dependents();
   const int n = p.dims[0];
   const int off = (lift_mode == KMPC_LIFT_STACK) ? n : 0;
-  const int gid = lane >> 2, tig = lane & 3;   // mma fragment coordinates
-  const int mrow = 16 * (warp & 1);            // first row of this warp's two m-tiles
-  const int ng = warp >> 1;                    // n-tile group
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTileS;
     // layer-0 input, k-major, rows [n, inpad) zero
@@ -217,80 +134,13 @@ encoder_mma_kernel(EncParams p, const double* __restrict__ x, double* __restrict
       act[k * kActStride + r] = v;
     }
     __syncthreads();
-    for (int l = 0; l < p.n_layers; ++l) {
-      const int kin = p.inpad[l], out = p.dims[l + 1], ws = p.wstride[l];
-      const int nt = (out + 7) >> 3;
-      const bool last = (l == p.n_layers - 1);
-      mbar_wait(&bars[l], 0);  // layer l's weights have landed (returns at once after the first tile)
-      const double* wt = wsm + p.woff[l];
-      const double* bias = wt + kin * ws;
-      double c[2][4][2];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n0 = (ng + 4 * j) * 8;
-        const double b0 = (ng + 4 * j < nt) ? bias[n0 + 2 * tig] : 0.0;
-        const double b1 = (ng + 4 * j < nt) ? bias[n0 + 2 * tig + 1] : 0.0;
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          c[m][j][0] = b0;
-          c[m][j][1] = b1;
-        }
+    encoder_layers(p, act, act, wsm, bars, [&](int r, int col, double v) {
+      const int64_t row = row0 + r;
+      if (row < S) {
+        if (lift_mode != KMPC_LIFT_RAW) v -= p.z0[col];
+        z[row * out_dim + off + col] = v;
       }
-      const double* ap = act + tig * kActStride + mrow + gid;
-      const double* bp = wt + tig * ws + ng * 8 + gid;
-#pragma unroll 2
-      for (int k0 = 0; k0 < kin; k0 += 4) {
-        const double a0 = ap[k0 * kActStride];
-        const double a1 = ap[k0 * kActStride + 8];
-        double b[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = (ng + 4 * j < nt) ? bp[k0 * ws + 32 * j] : 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (ng + 4 * j < nt) {  // warp-uniform
-            dmma_m8n8k4(c[0][j][0], c[0][j][1], a0, b[j]);
-            dmma_m8n8k4(c[1][j][0], c[1][j][1], a1, b[j]);
-          }
-        }
-      }
-      __syncthreads();  // every warp has finished reading the activations of this layer
-      if (!last) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (ng + 4 * j < nt) {
-            const int col = (ng + 4 * j) * 8 + 2 * tig;
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              const int r = mrow + 8 * m + gid;
-              act[col * kActStride + r] = fmax(c[m][j][0], 0.0);
-              act[(col + 1) * kActStride + r] = fmax(c[m][j][1], 0.0);
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (ng + 4 * j < nt) {
-            const int col = (ng + 4 * j) * 8 + 2 * tig;
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              const int64_t row = row0 + mrow + 8 * m + gid;
-              if (row < S) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                  if (col + q < out) {
-                    double v = c[m][j][q];
-                    if (lift_mode != KMPC_LIFT_RAW) v -= p.z0[col + q];
-                    z[row * out_dim + off + col + q] = v;
-                  }
-                }
-              }
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
+    });
   }
 }
 
@@ -335,16 +185,6 @@ encoder_kernel(EncParams p, const double* __restrict__ x, double* __restrict__ z
 
 using namespace kmpc;
 
-struct kmpc_encoder {
-  EncParams p;
-  int smem_bytes = 0;      // dynamic smem of encoder_smem_kernel (0: does not fit, use fallback)
-  int num_sms = 148;
-  std::vector<double*> owned;
-  double* d_z0 = nullptr;
-  // L2-resident lift workspace for kmpc_gram_from_snapshots (allocated on first use)
-  double* d_ws = nullptr;
-  int64_t ws_rows = 0;
-};
 
 static int launch_encoder(const kmpc_encoder* enc, const double* x, double* z, int64_t S,
                           int lift_mode, cudaStream_t st) {
@@ -440,6 +280,7 @@ int kmpc_encoder_create(kmpc_encoder** out, const double* const* W, const double
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&enc->num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    enc->max_smem_optin = max_smem;
     const size_t need = ((size_t)actw * kActStride + packed.size()) * sizeof(double) + KMPC_MAX_LAYERS * 8;
     enc->smem_bytes = (need <= (size_t)max_smem) ? (int)need : 0;
   }

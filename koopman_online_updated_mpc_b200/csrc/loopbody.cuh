@@ -11,6 +11,7 @@ struct LoopDev {  // passed by value to the kernels
   kmpc_loop_buffers b;
   double* z_next;  // ctx-owned (S, nz): lift(x+)
   double* x_prev;  // ctx-owned (S, n):  x before the plant step (tank C regression)
+  unsigned int* wset;  // ctx-owned (S, 2): optimal QP working set of the last step (fused kernel warm start)
 };
 
 KMPC_HD inline int loop_nzq(const kmpc_loop_config& c) { return c.nz + (c.du_aug ? 1 : 0); }

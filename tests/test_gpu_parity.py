@@ -278,3 +278,61 @@ def test_launch_counter_counts_kernels():
     before = K.launch_count()
     K.lift.rbf(np.zeros((4, 2)), np.ones((8, 2)))
     assert K.launch_count() == before + 1
+
+
+# ------------------------------------------------------------------------------ fused kernel ---
+@pytest.mark.parametrize("name,T", [("duffing", 150), ("duffing_frozen", 130), ("vdp", 150), ("vdp_frozen", 110),
+                                    ("duffing_rbf_frozen", 110)])
+def test_fused_kernel_matches_generic_three_kernel_path(name, T, monkeypatch):
+    """The persistent fused kernel (fused.cu: state in registers, T steps per launch) against the
+    generic qp_plant -> lift -> rls kernels (closed_loop.cu) on the same scenarios."""
+    case = cases.loop_case(name)
+    fused = _run_cuda(case, T)
+    monkeypatch.setenv("KMPC_FUSED", "0")
+    generic = _run_cuda(case, T)
+    monkeypatch.delenv("KMPC_FUSED")
+    assert np.array_equal(fused["status"], generic["status"])
+    # same bar as against the oracle (cases.loop_tolerances): the RLS restart makes the first steps
+    # of the update loops amplify rounding differences between the two arithmetic orders
+    xa, ua, ul = cases.loop_tolerances("update" if case["update"] else "frozen")
+    late = slice(3 * T // 4, T)
+    assert np.abs(fused["log_x"] - generic["log_x"]).max() <= xa
+    assert np.abs(fused["log_u"] - generic["log_u"]).max() <= ua
+    assert np.abs(fused["log_u"][late] - generic["log_u"][late]).max() <= ul * max(1.0, np.abs(generic["log_u"][late]).max())
+    for k in ("A", "B", "C"):
+        scale = np.abs(generic[k]).max()
+        np.testing.assert_allclose(fused[k], generic[k], rtol=0, atol=1e-4 * scale)
+    lf, lg = fused["loop"], generic["loop"]
+    np.testing.assert_allclose(lf.z.cpu().numpy(), lg.z.cpu().numpy(), rtol=0, atol=xa)
+    if lf.rls is not None:
+        for k in ("KA", "P", "barX", "barQ"):
+            a, b = getattr(lf.rls, k).cpu().numpy(), getattr(lg.rls, k).cpu().numpy()
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-4 * np.abs(b).max())
+
+
+def test_fused_kernel_ragged_tiles_and_single_steps():
+    """S not a multiple of the 32-scenario tile; T = 1 launches equal one T = 40 launch bit for bit."""
+    Ws, bs = H.oracle_weights("vdp")
+    g = H.golden("ref_vanderpol.npz")
+    enc = K.Encoder(Ws, bs)
+    rs = np.random.default_rng(5)
+    S, T = 77, 40
+    x0 = rs.uniform(-1.5, 1.5, (S, 2))
+    r = enc(np.stack([rs.uniform(-1, 1, S), np.zeros(S)], axis=1))
+    one = K.ClosedLoop(K.vanderpol_spec(), x0, g["A"], g["B"], g["C"], r, encoder=enc, log_steps=T).run(T)
+    many = K.ClosedLoop(K.vanderpol_spec(), x0, g["A"], g["B"], g["C"], r, encoder=enc, log_steps=T)
+    for _ in range(T):
+        many.run(1)
+    torch.cuda.synchronize()
+    assert np.array_equal(one.log_x.cpu().numpy(), many.log_x.cpu().numpy())
+    assert np.array_equal(one.rls.P.cpu().numpy(), many.rls.P.cpu().numpy())
+    assert one.step_index == T and int(one.status.max().item()) == 0
+
+
+def test_fused_timed_phases_sum_below_launch_time():
+    case = cases.loop_case("vdp")
+    enc = K.Encoder(case["Ws"], case["bs"])
+    loop = K.ClosedLoop(case["spec"], case["x0"], case["A"], case["B"], case["C"], case["r"], encoder=enc)
+    loop.run(5)
+    ms = loop.run_timed(20)
+    assert all(v > 0 for v in ms.values()) and loop.step_index == 25
