@@ -202,10 +202,23 @@ int kmpc_ctx_destroy(kmpc_ctx* ctx);
 /* run T scenario-steps for all S scenarios; continues from the ctx's step index */
 int kmpc_closed_loop_steps(kmpc_ctx* ctx, int T, void* stream);
 int64_t kmpc_ctx_step_index(const kmpc_ctx* ctx);
-/* same as kmpc_closed_loop_steps (T <= 1024) but brackets every kernel with CUDA events on
- * `stream` and returns, after synchronising, the summed device time in milliseconds of
- * ms[0] = QP+plant kernels, ms[1] = lift kernels, ms[2] = RLS kernels (bench.py's roofline) */
+/* start a new episode on the same buffers: step index <- 0, RLS restart pending again unless
+ * rls_started, QP warm-start memory cleared.  The caller rewrites x, z, u_prev, A, B, C (and the
+ * RLS state when warm-starting) -- the loop `for i in range(maxStep)` begins again (duffing.py:823) */
+int kmpc_ctx_reset(kmpc_ctx* ctx, int rls_started, void* stream);
+/* 1 when kmpc_closed_loop_steps runs as ONE persistent fused kernel per call (nz = 8, N = 10 loops),
+ * 0 when it runs the generic qp_plant -> lift -> rls kernels once per step */
+int kmpc_ctx_is_fused(const kmpc_ctx* ctx);
+/* same as kmpc_closed_loop_steps but also returns, after synchronising, the device time in
+ * milliseconds spent in ms[0] = QP+plant, ms[1] = lift, ms[2] = RLS (bench.py's roofline):
+ * CUDA events around every kernel on the generic path (T <= 1024), per-phase clock64() sums
+ * scaled to the event-timed launch on the fused path */
 int kmpc_closed_loop_steps_timed(kmpc_ctx* ctx, int T, void* stream, float* ms);
+
+/* ------------------------------------------------------------------ roofline denominators ----
+ * MEASURED_PEAKS.json carries no fp64 number: measure this GPU's fp64 tensor-path
+ * (mma.sync.m8n8k4.f64) and CUDA-core (DFMA) peaks, TFLOP/s, ~25 ms each; synchronises. */
+int kmpc_measure_fp64_peak(double* dmma_tflops, double* dfma_tflops, void* stream);
 
 #ifdef __cplusplus
 }

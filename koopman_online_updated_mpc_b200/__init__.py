@@ -12,7 +12,7 @@ the reference's call sites (duffing.py / vanderpol.py / duffing_RBF.py / Tank_Sy
     closed_loop.ClosedLoop(...).run(T)        fused scenario steps (duffing.py:823-992)
 """
 from . import closed_loop, distributed, edmd, lift, mpc, plant, rls, weights  # noqa: F401
-from ._lib import KmpcError, launch_count, lib  # noqa: F401
+from ._lib import KmpcError, launch_count, lib, measure_fp64_peak  # noqa: F401
 from .build import build  # noqa: F401
 from .closed_loop import ClosedLoop, LoopSpec, duffing_spec, rbf_spec, tank_spec, vanderpol_spec  # noqa: F401
 from .lift import Encoder, rbf  # noqa: F401

@@ -50,6 +50,9 @@ _PROTOS = {
     "kmpc_ctx_destroy": (_i, [_vp]),
     "kmpc_closed_loop_steps": (_i, [_vp, _i, _vp]),
     "kmpc_ctx_step_index": (_i64, [_vp]),
+    "kmpc_ctx_reset": (_i, [_vp, _i, _vp]),
+    "kmpc_ctx_is_fused": (_i, [_vp]),
+    "kmpc_measure_fp64_peak": (_i, [_c.POINTER(_d), _c.POINTER(_d), _vp]),
     "kmpc_closed_loop_steps_timed": (_i, [_vp, _i, _vp, _c.POINTER(_c.c_float)]),
 }
 
@@ -83,3 +86,11 @@ def check(rc):
 
 def launch_count():
     return int(lib().kmpc_launch_count())
+
+
+def measure_fp64_peak():
+    """(dmma_tflops, dfma_tflops) of the current GPU: the fp64 roofline denominators (synchronises)."""
+    import torch
+    a, b = _d(), _d()
+    check(lib().kmpc_measure_fp64_peak(_c.byref(a), _c.byref(b), torch.cuda.current_stream().cuda_stream))
+    return a.value, b.value

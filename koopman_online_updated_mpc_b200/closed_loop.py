@@ -153,6 +153,9 @@ class ClosedLoop:
                 self.rls, rls_started = rls_state, 1
             else:
                 self.rls = RLSState(S, nz, n, spec.p0, spec.q0)
+        # initial values kept for reset()
+        self._x0, self._A0, self._B0, self._C0 = self.x.clone(), self.A.clone(), self.B.clone(), self.C.clone()
+        self._u0 = self.u_prev.clone()
         self.log_x = torch.zeros((log_steps, S, n), **f64) if log_steps else None
         self.log_u = torch.zeros((log_steps, S), **f64) if log_steps else None
         self.status = torch.zeros(S, dtype=torch.int32, device="cuda")
@@ -170,6 +173,38 @@ class ClosedLoop:
                                      encoder.handle if spec.lift_kind == LIFTKIND_MLP else None,
                                      rls_started, stream_ptr()))
         self._h = h
+
+    @property
+    def fused(self):
+        """True when run(T) is ONE persistent fused kernel launch (nz = 8, N = 10 loops)."""
+        return bool(_lib.lib().kmpc_ctx_is_fused(self._h))
+
+    def reset(self, x0=None, rls_state=None):
+        """Start a new episode on the same device buffers (the reference's `for i in range(maxStep)`
+        begins again): x <- x0 (default: the x0 of construction), z <- lift(x), u_prev <- 0,
+        A, B, C <- the initial model, step index <- 0, RLS restart pending again (or warm state)."""
+        L = _lib.lib()
+        spec = self.spec
+        if x0 is not None:
+            self._x0.copy_(to_dev(x0).reshape(self.S, spec.n), non_blocking=True)
+        self.x.copy_(self._x0)
+        self.A.copy_(self._A0)
+        self.B.copy_(self._B0)
+        self.C.copy_(self._C0)
+        self.u_prev.copy_(self._u0)
+        self.status.zero_()
+        if spec.lift_kind == LIFTKIND_MLP:
+            self.encoder.encode_into(self.x, self.z, spec.lift_mode)
+        else:
+            _lib.check(L.kmpc_rbf_lift(ptr(self.x), ptr(self.cx), ptr(self.z), self.S, spec.n, spec.nz,
+                                       spec.lift_mode, stream_ptr()))
+        started = 0
+        if spec.update and rls_state is not None:
+            for k in ("KA", "P", "barX", "barQ"):
+                getattr(self.rls, k).copy_(getattr(rls_state, k))
+            started = 1
+        _lib.check(L.kmpc_ctx_reset(self._h, started, stream_ptr()))
+        return self
 
     @property
     def step_index(self):

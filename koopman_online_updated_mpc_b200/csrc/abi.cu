@@ -11,9 +11,77 @@ int record_cuda_error(cudaError_t e, const char* what, const char* file, int lin
   cudaGetLastError();  // clear the (non-sticky) last-error slot so later launches are not blamed
   return KMPC_ERR_CUDA;
 }
+
+// ---- fp64 peak probes (roofline denominators; same kernels as profiles/tools/fp64_peak.cu) ------
+__global__ void peak_dfma_kernel(double* out, int iters) {
+  double a[8], x = 1.0000001, y = 0.9999999;
+  for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 1e-9 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fma(a[i], x, y);
+  }
+  double s = 0;
+  for (int i = 0; i < 8; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void peak_dmma_kernel(double* out, int iters) {
+  double c[4][2], a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int i = 0; i < 4; ++i) c[i][0] = c[i][1] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1])
+                   : "d"(a), "d"(b));
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = c[0][0] + c[1][1] + c[2][0] + c[3][1];
+}
 }  // namespace kmpc
 
 extern "C" {
+
+int kmpc_measure_fp64_peak(double* dmma_tflops, double* dfma_tflops, void* stream) {
+  using namespace kmpc;
+  if (!dmma_tflops || !dfma_tflops) return KMPC_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  int dev = 0, sms = 0;
+  KMPC_CUDA(cudaGetDevice(&dev));
+  KMPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int iters = 20000, blocks = sms * 8, threads = 512;
+  double* out = nullptr;
+  KMPC_CUDA(cudaMalloc(&out, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  KMPC_CUDA(cudaEventCreate(&e0));
+  KMPC_CUDA(cudaEventCreate(&e1));
+  float best_f = 1e30f, best_m = 1e30f;
+  int rc = KMPC_OK;
+  for (int rep = 0; rep < 3 && rc == KMPC_OK; ++rep) {
+    float ms = 0.f;
+    cudaEventRecord(e0, st);
+    peak_dfma_kernel<<<blocks, threads, 0, st>>>(out, iters);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess) rc = KMPC_ERR_CUDA;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep && ms < best_f) best_f = ms;
+    cudaEventRecord(e0, st);
+    peak_dmma_kernel<<<blocks, threads, 0, st>>>(out, iters);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess) rc = KMPC_ERR_CUDA;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep && ms < best_m) best_m = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (rc != KMPC_OK) return record_cuda_error(cudaGetLastError(), "fp64 peak probe", __FILE__, __LINE__);
+  *dfma_tflops = 2.0 * 32.0 * iters * (double)blocks * threads / best_f * 1e-9;
+  *dmma_tflops = 2.0 * 256.0 * 4.0 * iters * (double)blocks * (threads / 32) / best_m * 1e-9;
+  return KMPC_OK;
+}
 
 const char* kmpc_strerror(int code) {
   switch (code) {

@@ -199,6 +199,17 @@ int kmpc_ctx_destroy(kmpc_ctx* ctx) {
 
 int64_t kmpc_ctx_step_index(const kmpc_ctx* ctx) { return ctx ? ctx->step : -1; }
 
+int kmpc_ctx_is_fused(const kmpc_ctx* ctx) { return (ctx && ctx->fused) ? 1 : 0; }
+
+int kmpc_ctx_reset(kmpc_ctx* ctx, int rls_started, void* stream) {
+  if (!ctx) return KMPC_ERR_ARG;
+  ctx->step = 0;
+  ctx->rls_started = rls_started;
+  if (ctx->d.wset)
+    KMPC_CUDA(cudaMemsetAsync(ctx->d.wset, 0, (size_t)ctx->d.c.S * 2 * sizeof(unsigned int), as_stream(stream)));
+  return KMPC_OK;
+}
+
 // One closed-loop step = qp_plant kernel -> lift kernel -> (rls kernel).  `ev` (nullable) points at
 // 4 events recorded around the three launches (kmpc_closed_loop_steps_timed).
 static int run_one_step(kmpc_ctx* ctx, void* stream, cudaEvent_t* ev) {

@@ -69,6 +69,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
+// ReLU that propagates NaN like torch.nn.ReLU / numpy.maximum (fmax would return 0 for NaN)
+__device__ __forceinline__ double relu_nan(double v) { return v < 0.0 ? 0.0 : v; }
+
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
@@ -166,8 +169,8 @@ __device__ __forceinline__ void encoder_layers(const EncParams& p, const double*
         for (int m = 0; m < 2; ++m) {
           const int r = mrow + 8 * m + gid;
           if (!last) {
-            act[col * kActStride + r] = fmax(c[m][j][0], 0.0);
-            act[(col + 1) * kActStride + r] = fmax(c[m][j][1], 0.0);
+            act[col * kActStride + r] = relu_nan(c[m][j][0]);
+            act[(col + 1) * kActStride + r] = relu_nan(c[m][j][1]);
           } else {
             if (col < out) store(r, col, c[m][j][0]);
             if (col + 1 < out) store(r, col + 1, c[m][j][1]);
@@ -176,6 +179,87 @@ __device__ __forceinline__ void encoder_layers(const EncParams& p, const double*
       }
     }
     __syncthreads();
+  }
+}
+// ---- quarter-CTA variant (fused.cu): a group of 2 warps lifts ITS 8 scenarios (one m-tile) on its
+// own, synchronising only with its partner warp through a named barrier, so the four quarters of a
+// CTA drift freely and the tensor-pipe phases of one quarter overlap the latency-bound QP / RLS
+// phases of the others.  Warp wl (0/1) of the quarter owns the n-tiles wl, wl + 2, wl + 4, ...
+constexpr int kQRows = 8;
+constexpr int kQStride = 12;       // doubles per activation row k: 8 scenarios + 4 pad (== 12 mod 16)
+constexpr int kQMaxTiles = (KMPC_MAX_WIDTH / 8 + 1) / 2;   // n-tiles per warp at the widest layer
+
+__device__ __forceinline__ void quarter_barrier(int id) {
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+
+template <int NT>
+__device__ __forceinline__ void encoder_kloop_q(const double* __restrict__ ap, const double* __restrict__ bp,
+                                                int kin, int ws, double (&c)[kQMaxTiles][2]) {
+#pragma unroll 2
+  for (int k0 = 0; k0 < kin; k0 += 4) {
+    const double a = ap[k0 * kQStride];
+    double b[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) b[j] = bp[k0 * ws + 16 * j];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) dmma_m8n8k4(c[j][0], c[j][1], a, b[j]);
+  }
+}
+
+// in0: layer-0 input of the quarter, k-major in0[k * kQStride + row] (rows [n, inpad[0]) zero);
+// act: the quarter's activation buffer (actw * kQStride doubles); bar_id: the quarter's barrier.
+// The caller synchronises the quarter before the call; ends with a quarter barrier.
+template <typename Store>
+__device__ __forceinline__ void encoder_layers_q(const EncParams& p, const double* in0, double* act,
+                                                 const double* wsm, uint64_t* bars, int wl, int bar_id,
+                                                 Store store) {
+  const int lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;   // mma fragment coordinates
+  for (int l = 0; l < p.n_layers; ++l) {
+    const int kin = p.inpad[l], out = p.dims[l + 1], ws = p.wstride[l];
+    const int nt = (out + 7) >> 3;
+    const bool last = (l == p.n_layers - 1);
+    mbar_wait(&bars[l], 0);
+    const double* wt = wsm + p.woff[l];
+    const double* bias = wt + kin * ws;
+    double c[kQMaxTiles][2];
+#pragma unroll
+    for (int j = 0; j < kQMaxTiles; ++j) {
+      const int tile = wl + 2 * j;
+      c[j][0] = (tile < nt) ? bias[tile * 8 + 2 * tig] : 0.0;
+      c[j][1] = (tile < nt) ? bias[tile * 8 + 2 * tig + 1] : 0.0;
+    }
+    const double* ap = (l == 0 ? in0 : act) + tig * kQStride + gid;
+    const double* bp = wt + tig * ws + wl * 8 + gid;
+    const int my_nt = (nt > wl) ? ((nt - wl + 1) >> 1) : 0;   // warp-uniform
+    switch (my_nt) {
+      case 8: encoder_kloop_q<8>(ap, bp, kin, ws, c); break;
+      case 7: encoder_kloop_q<7>(ap, bp, kin, ws, c); break;
+      case 6: encoder_kloop_q<6>(ap, bp, kin, ws, c); break;
+      case 5: encoder_kloop_q<5>(ap, bp, kin, ws, c); break;
+      case 4: encoder_kloop_q<4>(ap, bp, kin, ws, c); break;
+      case 3: encoder_kloop_q<3>(ap, bp, kin, ws, c); break;
+      case 2: encoder_kloop_q<2>(ap, bp, kin, ws, c); break;
+      case 1: encoder_kloop_q<1>(ap, bp, kin, ws, c); break;
+      default: break;
+    }
+    quarter_barrier(bar_id);   // both warps have finished reading the activations of this layer
+#pragma unroll
+    for (int j = 0; j < kQMaxTiles; ++j) {
+      const int tile = wl + 2 * j;
+      if (tile < nt) {
+        const int col = tile * 8 + 2 * tig;
+        if (!last) {
+          act[col * kQStride + gid] = relu_nan(c[j][0]);
+          act[(col + 1) * kQStride + gid] = relu_nan(c[j][1]);
+        } else {
+          if (col < out) store(gid, col, c[j][0]);
+          if (col + 1 < out) store(gid, col + 1, c[j][1]);
+        }
+      }
+    }
+    quarter_barrier(bar_id);
   }
 }
 #endif  // __CUDACC__

@@ -41,13 +41,14 @@ constexpr int kRedPitch = 9;     // pitch of the 8 x 8 reduction buffer (conflic
 // scratch layout during the QP build and the RLS
 constexpr int oRED = 0;          // [8][kRedPitch] cross-lane reduction buffer
 constexpr int oEX = 72;          // 40 doubles: vector exchange (Krylov pairs / g,e / RLS gathers)
-constexpr int oHF = 112;         // 72 doubles: H packed lower triangle (55), f (10), pad
+constexpr int oHF = 112;         // 72 doubles: 2H packed lower triangle (55), f (10), pad
 // scratch layout during the QP solve (aliases RED/EX; HF stays live)
 constexpr int oL = 0;            // 60: strictly-lower factor + forward-substituted rhs, column major
 constexpr int oXS = 60;          // 10: current iterate x
 constexpr int oGS = 70;          // 10: gradient 2 H x + f
-constexpr int kIn0 = 4 * kActStride;   // layer-0 input block (k-major, 4 rows)
-constexpr int kZbuf = kTileS * FNZ;    // lift outputs of the tile
+constexpr int kZbuf = kTileS * FNZ;    // lift outputs of the tile (per quarter: 64 doubles, whose first
+                                       // 48 double as the quarter's layer-0 input block)
+static_assert(4 * kQStride <= kQRows * FNZ, "layer-0 input block aliases the quarter's lift outputs");
 
 // The identity-output build emits the 55 + 10 reduced values diagonal by diagonal (running sums
 // along a diagonal); this table maps emission number -> position in HF (packed lower triangle
@@ -66,16 +67,13 @@ __host__ __device__ constexpr int lcol(int j) {
 }
 
 struct FusedSmem {  // offsets in doubles from the start of dynamic shared memory
-  int scratch, zbuf, in0, wsm, bars, total_bytes;
+  int scratch, zbuf, wsm, bars, total_bytes;
 };
 inline FusedSmem fused_smem_layout(const EncParams* p) {
   FusedSmem L;
-  const int act = p ? p->actw * kActStride : 0;
-  const int scr = kTileS * kScr;
-  L.scratch = 0;
-  L.zbuf = (act > scr ? act : scr);
-  L.in0 = L.zbuf + kZbuf;
-  L.wsm = L.in0 + kIn0;
+  L.scratch = 0;                 // 32 x kScr; quarter q's activations alias scenarios 8q .. 8q+7
+  L.zbuf = kTileS * kScr;
+  L.wsm = L.zbuf + kZbuf;
   L.wsm = (L.wsm + 1) & ~1;
   L.bars = L.wsm + (p ? p->total_w : 0);
   L.bars = (L.bars + 1) & ~1;
@@ -121,7 +119,7 @@ __device__ __forceinline__ void group_gather(double* ex, int l, double mine, dou
 //   __syncwarp per column (the column is the exchange buffer).  The back substitution is done
 //   redundantly by every lane, which leaves the step p replicated in registers.
 struct QpCoop {
-  const double* HF;   // packed lower H (55) | f (10)
+  const double* HF;   // packed lower 2H (55) | f (10)
   double* sc;         // Lc (60) | xs (10) | gs (10)
   int l;              // lane within the scenario
   int status;
@@ -138,15 +136,19 @@ struct QpCoop {
     const int b0 = (r0 * (r0 + 1)) >> 1, b1 = (r1 < FN) ? (r1 * (r1 + 1)) >> 1 : 0;
     double a0[FNZ], a1[FN], dg[FN], invd[FN];
     int st = 0;
+    // all loads first (unconditional, clamped indices), the masks are applied with selects
+#pragma unroll
+    for (int k = 0; k < FN; ++k) {
+      if (k < FNZ) a0[k] = HF[b0 + min(k, r0)];
+      a1[k] = (l == 2) ? -gs[k] : HF[b1 + min(k, r1)];   // l == 2: the right-hand side row
+      dg[k] = HF[tri(k, k)];
+    }
 #pragma unroll
     for (int k = 0; k < FN; ++k) {
       const bool mk = (masked >> k) & 1u;
-      if (k < FNZ) a0[k] = (m0 || mk || k > r0) ? 0.0 : 2.0 * HF[b0 + (k <= r0 ? k : 0)];
-      double v1;
-      if (r1 < FN) v1 = (m1 || mk || k > r1) ? 0.0 : 2.0 * HF[b1 + (k <= r1 ? k : 0)];
-      else v1 = mk ? 0.0 : -gs[k];           // right-hand side row
-      a1[k] = has1 ? v1 : 0.0;
-      dg[k] = mk ? 1.0 : 2.0 * HF[tri(k, k)];
+      if (k < FNZ) a0[k] = (m0 || mk || k > r0) ? 0.0 : a0[k];
+      a1[k] = (!has1 || mk || m1 || (r1 < FN && k > r1)) ? 0.0 : a1[k];
+      dg[k] = mk ? 1.0 : dg[k];
     }
 #pragma unroll
     for (int j = 0; j < FN; ++j) {
@@ -211,7 +213,7 @@ struct QpCoop {
           s0 = fma(HF[j <= r ? br + j : tri(j, 0) + r], xv[j], s0);
           s1 = fma(HF[j + 1 <= r ? br + j + 1 : tri(j + 1, 0) + r], xv[j + 1], s1);
         }
-        gs[r] = fma(2.0, s0 + s1, HF[55 + r]);
+        gs[r] = (s0 + s1) + HF[55 + r];
       }
     }
     __syncwarp();
@@ -388,13 +390,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
   extern __shared__ __align__(16) double smem[];
   const kmpc_loop_config& c = a.d.c;
   const kmpc_loop_buffers& b = a.d.b;
-  double* zbuf = smem + a.sm.zbuf;
-  double* in0 = smem + a.sm.in0;
   double* wsm = smem + a.sm.wsm;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.sm.bars);
   const int tid = threadIdx.x;
   const int sc = tid >> 3, l = tid & 7;
   double* scr = smem + a.sm.scratch + sc * kScr;
+  // quarter = 2 warps = 8 scenarios: its own activation buffer (aliasing its scenarios' scratch),
+  // lift outputs and named barrier; quarters never wait for each other inside the step loop
+  const int quarter = tid >> 6, wl = (tid >> 5) & 1, qbar = 1 + quarter;
+  double* qact = smem + a.sm.scratch + quarter * (kQRows * kScr);
+  double* qz = smem + a.sm.zbuf + quarter * (kQRows * FNZ);
   double* red = scr + oRED;
   double* ex = scr + oEX;
   double* HF = scr + oHF;
@@ -539,12 +544,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
 #pragma unroll
           for (int k = 0; k + dd < FN; ++k) {
             run = fma(VB[k + dd], VB[k], run);
-            ch[n & 7] = c.q * run;
+            ch[n & 7] = (2.0 * c.q) * run;
             ++n;
             if ((n & 7) == 0) {
               const double sum = chunk_reduce(red, l, ch);
               const int idx = n - 8 + l;
-              HF[c_hf_tab[idx]] = sum + (idx < FN ? c.rw : 0.0);
+              HF[c_hf_tab[idx]] = sum + (idx < FN ? 2.0 * c.rw : 0.0);
             }
           }
         }
@@ -604,7 +609,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
                 run = fma(g1.x, g0.x, run);
                 run = fma(g1.y, g0.y, run);
                 const int ra = FN - 1 - k;   // H[ra][ra - dd]
-                HF[((ra * (ra + 1)) >> 1) + ra - dd] = c.q * run + (dd == 0 ? c.rw : 0.0);
+                HF[((ra * (ra + 1)) >> 1) + ra - dd] = 2.0 * (c.q * run + (dd == 0 ? c.rw : 0.0));
               }
             } else {
               double sacc = 0.0;  // f[a], a = dd
@@ -639,6 +644,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
 #pragma unroll
           for (int k = 0; k < 5; ++k) prm[k] = __ldg(pp + k);
           plant_step_dev(c.plant_kind, c.rk4_variant, c.h, prm, x1, x2, unew, x1n, x2n);
+          if (!isfinite(x1n) || !isfinite(x2n)) status |= KMPC_STATUS_NONFINITE;   // plant left the reals
           if (valid) {
             const int64_t slot = (step < b.log_capacity) ? step : -1;
             if (b.log_x && slot >= 0) {
@@ -657,12 +663,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
       // ================= lift(x+) =================
       double yl;
       if (MLP) {
-        if (l < 4) in0[l * kActStride + sc] = (l == 0) ? x1n : ((l == 1) ? x2n : 0.0);
-        __syncthreads();
+        // both warps of the quarter are past their last read of qz (the previous lift) and of the
+        // scratch their activations are about to overwrite
+        quarter_barrier(qbar);
+        if (l < 4) qz[l * kQStride + (sc & 7)] = (l == 0) ? x1n : ((l == 1) ? x2n : 0.0);
+        quarter_barrier(qbar);
         if (TIMED) tq += clock64() - c0, c0 = clock64();
         if (!(a.dbg_skip & 2))
-          encoder_layers(a.p, in0, smem, wsm, bars, [&](int r, int col, double v) { zbuf[r * FNZ + col] = v; });
-        yl = zbuf[sc * FNZ + l];
+          encoder_layers_q(a.p, qz, qact, wsm, bars, wl, qbar,
+                           [&](int r, int col, double v) { qz[r * FNZ + col] = v; });
+        yl = qz[(sc & 7) * FNZ + l];
         if (c.lift_mode != KMPC_LIFT_RAW) yl -= a.p.z0[l];
         if (TIMED) tl += clock64() - c0, c0 = clock64();
       } else {
@@ -805,7 +815,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
         }
       }
     }
-    __syncthreads();  // the next tile reuses scratch / zbuf
+    quarter_barrier(qbar);  // the next tile reuses the quarter's scratch / lift outputs
   }
   if (TIMED && tid == 0) {
     a.timing[blockIdx.x * 4 + 0] = tq;
@@ -843,6 +853,7 @@ bool fused_eligible(const kmpc_loop_config& c, const kmpc_encoder* enc) {
     if (!enc || enc->smem_bytes <= 0) return false;
     if (c.lift_mode == KMPC_LIFT_STACK) return false;
     if (enc->p.dims[0] != 2 || enc->p.dims[enc->p.n_layers] != FNZ) return false;
+    if (enc->p.actw * kQStride > kQRows * kScr) return false;   // a quarter's activations alias its scratch
     const FusedSmem L = fused_smem_layout(&enc->p);
     if (L.total_bytes > enc->max_smem_optin) return false;
   } else if (c.lift_kind != KMPC_LIFTKIND_RBF) {

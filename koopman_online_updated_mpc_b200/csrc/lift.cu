@@ -76,10 +76,10 @@ __device__ __forceinline__ void enc_store_tile(const double (&acc)[4][4], bool l
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       double2 o01, o23;
-      o01.x = fmax(acc[0][c], 0.0);
-      o01.y = fmax(acc[1][c], 0.0);
-      o23.x = fmax(acc[2][c], 0.0);
-      o23.y = fmax(acc[3][c], 0.0);
+      o01.x = (acc[0][c] < 0.0 ? 0.0 : acc[0][c]);
+      o01.y = (acc[1][c] < 0.0 ? 0.0 : acc[1][c]);
+      o23.x = (acc[2][c] < 0.0 ? 0.0 : acc[2][c]);
+      o23.y = (acc[3][c] < 0.0 ? 0.0 : acc[3][c]);
       double* op = act_out + (4 * cg + c) * kTileS + 4 * rg;
       *reinterpret_cast<double2*>(op) = o01;
       *reinterpret_cast<double2*>(op + 2) = o23;

@@ -101,7 +101,8 @@ KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, const LoopShape sh, int64
       d.b.log_x[(log_slot * c.S + s) * 2 + 1] = o2;
     }
     if (d.b.log_u && log_slot >= 0) d.b.log_u[log_slot * c.S + s] = u;
-    if (d.b.status && st) d.b.status[s] |= st;
+    const int st2 = st | ((isfinite(o1) && isfinite(o2)) ? 0 : KMPC_STATUS_NONFINITE);   // plant left the reals
+    if (d.b.status && st2) d.b.status[s] |= st2;
   }
 }
 

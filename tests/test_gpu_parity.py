@@ -336,3 +336,47 @@ def test_fused_timed_phases_sum_below_launch_time():
     loop.run(5)
     ms = loop.run_timed(20)
     assert all(v > 0 for v in ms.values()) and loop.step_index == 25
+
+
+def test_reset_starts_an_identical_episode():
+    case = cases.loop_case("vdp")
+    enc = K.Encoder(case["Ws"], case["bs"])
+    T = 80
+    loop = K.ClosedLoop(case["spec"], case["x0"], case["A"], case["B"], case["C"], case["r"], encoder=enc, log_steps=T)
+    assert loop.fused
+    first = loop.run(T).log_x.clone()
+    P1 = loop.rls.P.clone()
+    loop.reset().run(T)
+    assert loop.step_index == T
+    assert torch.equal(first, loop.log_x) and torch.equal(P1, loop.rls.P)
+    x1 = np.array([[0.3, -0.2], [1.0, 1.0], [-0.5, 0.7]])
+    loop.reset(x1).run(T)
+    fresh = K.ClosedLoop(case["spec"], x1, case["A"], case["B"], case["C"], case["r"], encoder=enc, log_steps=T).run(T)
+    assert torch.equal(fresh.log_x, loop.log_x)
+
+
+def test_plant_blow_up_matches_the_reference_arithmetic():
+    """x0 near (-2, -1.3) with a far set-point drives |x1| past 2.4, where the reference's RK4 plant
+    (h = 0.05) is numerically unstable: the oracle and the kernel must diverge the same way (same
+    trajectory until the blow-up, non-finite within a step of each other, flagged, not aborted)."""
+    Ws, bs = H.oracle_weights("vdp")
+    g = H.golden("ref_vanderpol.npz")
+    enc = K.Encoder(Ws, bs)
+    x0 = np.array([[-1.9679426952760442, -1.2564560344690783], [0.5, 0.5]])
+    xref = np.array([[0.8085404454242318, 0.0], [0.2, 0.0]])
+    T = 90
+    loop = K.ClosedLoop(K.vanderpol_spec(), x0, g["A"], g["B"], g["C"], enc(xref), encoder=enc, log_steps=T).run(T)
+    lx, st = loop.log_x.cpu().numpy(), loop.status.cpu().numpy()
+    with np.errstate(all="ignore"):
+        o = ocl.run_loop(ocl.vanderpol_config(Ws, bs, xref[0]), g["A"], g["B"], g["C"], x0[0], T, update=ocl.UPDATE_RLS,
+                         qp="exact")
+    bad_gpu = int(np.argmax(~np.isfinite(lx[:, 0]).all(axis=1)))
+    bad_ref = int(np.argmax(~np.isfinite(o["X"]).all(axis=1)))
+    assert bad_gpu > 0 and abs(bad_gpu - bad_ref) <= 1
+    assert np.abs(lx[:65, 0] - o["X"][:65]).max() < 1e-4
+    assert st[0] & 2 and st[1] == 0 and np.isfinite(lx[:, 1]).all()      # the healthy neighbour is untouched
+
+
+def test_fp64_peak_probe():
+    dmma, dfma = K.measure_fp64_peak()
+    assert 5.0 < dmma < 100.0 and 5.0 < dfma < 100.0
