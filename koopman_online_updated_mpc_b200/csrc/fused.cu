@@ -153,9 +153,10 @@ struct QpCoop {
 #pragma unroll
     for (int j = 0; j < FN; ++j) {
       double d = dg[j];
-      if (!(d > 0.0)) {
+      const double floor_j = ((masked >> j) & 1u) ? 0.0 : kPivotFloor * HF[tri(j, j)];
+      if (!(d > floor_j)) {  // numerically semi-definite: regularise and flag (oracle/mpc.py PIVOT_FLOOR)
         st |= KMPC_STATUS_PIVOT;
-        d = 1e-300;
+        d = floor_j;
       }
       const double inv = rsqrt(d);
       invd[j] = inv;

@@ -51,6 +51,10 @@ inline double rsqrt(double v) { return 1.0 / sqrt(v); }
 
 namespace kmpc {
 
+// a Cholesky pivot below kPivotFloor * (its original diagonal entry) is replaced by that floor and
+// flagged KMPC_STATUS_PIVOT: the Tank Delta-u Hessian reaches cond ~ 2e16 in the RLS transient
+constexpr double kPivotFloor = 1e-13;
+
 // ---------------------------------------------------------------- warp reductions -----------
 // Reductions over the G lanes of a group (xor offsets < G stay inside the aligned group);
 // host build: identity.  (value, index) argmin breaks ties towards the lowest index.
@@ -403,9 +407,10 @@ KMPC_DEV int qp_chol_masked(const QpWs& ws, int N) {
     }
     KMPC_SYNCWARP();
     double d = mj ? 1.0 : ws.L[tri(j, j)];
-    if (!(d > 0.0)) {
+    const double floor_j = mj ? 0.0 : kPivotFloor * (2.0 * ws.H[tri(j, j)]);
+    if (!(d > floor_j)) {  // numerically semi-definite: regularise and flag (oracle/mpc.py PIVOT_FLOOR)
       status |= KMPC_STATUS_PIVOT;
-      d = 1e-300;
+      d = floor_j;
     }
     const double inv = rsqrt(d);  // one MUFU + Newton instead of sqrt followed by a division
     const double piv = d * inv;
@@ -662,9 +667,10 @@ struct QpFast {
         if (i < N) ws.L[tri(i, j)] = s;   // publish the unscaled entry (row i is read when j == i)
         else ws.p[j] = s;                 // y_j
         if (i == j) {
-          if (!(s > 0.0)) {
+          const double floor_j = mj ? 0.0 : kPivotFloor * h2[j];
+          if (!(s > floor_j)) {
             status |= KMPC_STATUS_PIVOT;
-            s = 1e-300;
+            s = floor_j;
           }
           ws.invd[j] = __drcp_rn(s);
         }

@@ -68,6 +68,13 @@ def condense(A, B, Cy, z0, r, q, rw, N, PN=None):
     return H, f.reshape(-1)
 
 
+# relative pivot floor of the Cholesky factorisations (same constant in csrc/percase.cuh and
+# csrc/fused.cu): a pivot below PIVOT_FLOOR * (its original diagonal entry) is replaced by that
+# floor and flagged -- the Delta-u Hessian of Tank_System.m reaches cond ~ 2e16 while the restarted
+# RLS model is still rank deficient, where a plain Cholesky breaks down
+PIVOT_FLOOR = 1e-13
+
+
 def _masked_chol_solve(H2, rhs, free):
     """Solve H2[free,free] p = rhs[free] by Cholesky; returns p (zeros elsewhere), ok flag."""
     idx = np.flatnonzero(free)
@@ -79,9 +86,10 @@ def _masked_chol_solve(H2, rhs, free):
         L = np.zeros((n, n))
         for j in range(n):
             d = M[j, j] - L[j, :j] @ L[j, :j]
-            if not d > 0.0:
+            floor = PIVOT_FLOOR * M[j, j]
+            if not d > floor:       # numerically semi-definite (cond >~ 1e13): regularise, flag
                 ok = False
-                d = 1e-300
+                d = floor
             L[j, j] = np.sqrt(d)
             for i in range(j + 1, n):
                 L[i, j] = (M[i, j] - L[i, :j] @ L[j, :j]) / L[j, j]

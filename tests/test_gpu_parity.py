@@ -380,3 +380,94 @@ def test_plant_blow_up_matches_the_reference_arithmetic():
 def test_fp64_peak_probe():
     dmma, dfma = K.measure_fp64_peak()
     assert 5.0 < dmma < 100.0 and 5.0 < dfma < 100.0
+
+
+# ------------------------------------------------------------------------------ full sizes -----
+def test_full_size_edmd_snapshots_linearity():
+    """BASELINE config 4 shape on one GPU: 10 M duffing-like snapshots through the fused lift + Gram.
+    Size-independent properties: Gram(all) == Gram(first part) + Gram(rest) (what the all-reduce
+    relies on), the count, and A, B, C equal to the regression over a 10 k subsample within the
+    statistical tolerance of the snapshot distribution."""
+    Ws, bs = H.oracle_weights("duffing")
+    enc = K.Encoder(Ws, bs)
+    M = 10_000_000
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.rand((M, 2), generator=g, device="cuda", dtype=torch.float64) * 4 - 2
+    u = torch.rand(M, generator=g, device="cuda", dtype=torch.float64) * 4 - 2
+    y = K.plant.f_update(x, u, K.plant.DUFFING_PRE)
+    whole = K.edmd.gram_from_snapshots(enc, x, y, u)
+    cut = 3_333_337
+    parts = K.edmd.gram_from_snapshots(enc, x[:cut], y[:cut], u[:cut])
+    parts = K.edmd.gram_from_snapshots(enc, x[cut:], y[cut:], u[cut:], pack=parts)
+    assert float(whole[-1].item()) == M and float(parts[-1].item()) == M
+    np.testing.assert_allclose(parts.cpu().numpy(), whole.cpu().numpy(), rtol=1e-10)
+    A, B, C, st = K.edmd.edmd_solve(whole, 8, 2)
+    assert int(st.item()) == 0 and bool(torch.isfinite(A).all())
+    sub = slice(0, 20000)
+    xs, ys, us = x[sub].cpu().numpy(), y[sub].cpu().numpy(), u[sub].cpu().numpy()
+    Ao, Bo, Co = oedmd.edmd_pinv(olift.encoder_forward(Ws, bs, xs).T, olift.encoder_forward(Ws, bs, ys).T,
+                                 us.reshape(1, -1), xs.T)
+    assert np.abs(A.cpu().numpy() - Ao).max() < 0.05 * np.abs(Ao).max()
+    assert np.abs(C.cpu().numpy() - Co).max() < 0.05 * np.abs(Co).max()
+
+
+def test_full_size_tank_shard_properties():
+    """BASELINE config 3 shape: 65 536 tank scenarios (velocity form, N = 20) for a few steps on the
+    generic kernels: input and rate bounds respected, levels non-negative, finite, status clean,
+    and a shard of the batch reproduces its slice bit for bit."""
+    t = cases.tank_setup()
+    enc = K.Encoder(t["Ws"], t["bs"])
+    rs = np.random.default_rng(3)
+    S, T = 65536, 6
+    x0 = np.maximum(rs.uniform(0, 2, (S, 2)), 0.0)
+    loop = K.ClosedLoop(K.tank_spec(), x0, t["A"], t["B"], t["C"], np.array([1.0]), encoder=enc, log_steps=T).run(T)
+    assert not loop.fused
+    lx, lu, st = loop.log_x.cpu().numpy(), loop.log_u.cpu().numpy(), loop.status.cpu().numpy()
+    assert np.isfinite(lx).all() and np.isfinite(lu).all()
+    assert lx.min() >= 0.0
+    # no iteration cap, nothing non-finite; the rank-1 model of the very first RLS steps can make
+    # the Delta-u Hessian numerically semi-definite (cond ~ 2e16, SURVEY.md Appendix B), which the
+    # kernel flags as KMPC_STATUS_PIVOT instead of aborting: rare, and never fatal
+    assert ((st & 3) == 0).all(), np.unique(st)
+    assert (st != 0).mean() < 0.05, (st != 0).mean()
+    du = np.abs(np.diff(np.concatenate([np.zeros((1, S)), lu]), axis=0))
+    assert du.max() <= 0.5 + 1e-9 and np.abs(lu).max() <= 8.0 + 1e-9
+    sl = slice(40000, 40000 + 4099)
+    part = K.ClosedLoop(K.tank_spec(), x0[sl], t["A"], t["B"], t["C"], np.array([1.0]), encoder=enc, log_steps=T).run(T)
+    assert np.array_equal(part.log_x.cpu().numpy(), lx[:, sl])
+    # nearly empty tanks: at step 5 the restarted RLS model makes the Hessian numerically singular;
+    # the kernel and the oracle apply the same relative pivot floor and stay together
+    xs = np.array([[0.06378558970830861, 0.003204316873218982], [0.026345235171531645, 0.0067565715286719286]])
+    T2 = 60
+    hard = K.ClosedLoop(K.tank_spec(), xs, t["A"], t["B"], t["C"], np.array([1.0]), encoder=enc, log_steps=T2).run(T2)
+    hx, hs = hard.log_x.cpu().numpy(), hard.status.cpu().numpy()
+    assert np.isfinite(hx).all() and ((hs & 3) == 0).all()
+    for k in range(2):
+        o = ocl.run_loop(t["cfg"], t["A"], t["B"], t["C"], xs[k], T2, update=ocl.UPDATE_RLS, qp="exact")
+        assert np.abs(o["X"] - hx[:, k]).max() < 5e-3, k
+        assert np.abs(o["X"][40:] - hx[40:, k]).max() < 1e-5, k
+
+
+def test_full_size_rbf_horizon50_properties():
+    """BASELINE config 5 shape (per-GPU shard): 125 000 RBF-lifted duffing scenarios, horizon 50,
+    warm-started update, a few steps: bounds, finiteness, status, and scenario 0 against the oracle."""
+    g = H.golden("ref_duffing_rbf.npz")
+    X, Y, U = oplant.generate_snapshots(100, 100, oplant.DUFFING_PRE, np.random.RandomState(101))
+    PX, PY = olift.rbf_lift(X.T, g["cx"]).T, olift.rbf_lift(Y.T, g["cx"]).T
+    G, Aq, XV = oedmd.gram_pack(PX, PY, U, X)
+    rs = np.random.default_rng(9)
+    S, T = 125000, 4
+    x0 = rs.uniform(-2, 2, (S, 2))
+    x0[0] = [-2.0, -2.0]
+    warm = K.RLSState.warm(S, G, Aq, XV[:, :8], G[:8, :8])
+    spec = K.rbf_spec(N=50)
+    loop = K.ClosedLoop(spec, x0, g["A"], g["B"], g["C"], np.array([1.0, 0.0]), cx=g["cx"], rls_state=warm,
+                        log_steps=T).run(T)
+    lx, lu, st = loop.log_x.cpu().numpy(), loop.log_u.cpu().numpy(), loop.status.cpu().numpy()
+    assert np.isfinite(lx).all() and (st == 0).all()
+    assert lu.min() >= -2.0 - 1e-12 and lu.max() <= 2.0 + 1e-12
+    cfg = ocl.rbf_config(g["cx"])
+    cfg.N = 50
+    o = ocl.run_loop(cfg, g["A"], g["B"], g["C"], x0[0], T, update=ocl.UPDATE_RLS, qp="exact",
+                     warm=orls.RLSState.warm(G, Aq, XV[:, :8], G[:8, :8]))
+    assert np.abs(o["X"] - lx[:, 0]).max() < 1e-7
