@@ -181,85 +181,144 @@ __device__ __forceinline__ void encoder_layers(const EncParams& p, const double*
     __syncthreads();
   }
 }
-// ---- quarter-CTA variant (fused.cu): a group of 2 warps lifts ITS 8 scenarios (one m-tile) on its
-// own, synchronising only with its partner warp through a named barrier, so the four quarters of a
-// CTA drift freely and the tensor-pipe phases of one quarter overlap the latency-bound QP / RLS
-// phases of the others.  Warp wl (0/1) of the quarter owns the n-tiles wl, wl + 2, wl + 4, ...
-constexpr int kQRows = 8;
-constexpr int kQStride = 12;       // doubles per activation row k: 8 scenarios + 4 pad (== 12 mod 16)
-constexpr int kQMaxTiles = (KMPC_MAX_WIDTH / 8 + 1) / 2;   // n-tiles per warp at the widest layer
+// ---- lift-unit variant (fused.cu): a group of W warps lifts ITS unit of 8 scenarios (one m-tile),
+// synchronising only inside the group through a named barrier, so the units of a CTA drift freely.
+// Warp lw owns the n-tiles lw, lw + W, lw + 2W, ... of every hidden layer; activations ping-pong
+// between two k-major buffers of pitch 8 (ONE group barrier per layer); the k-loop is software
+// pipelined (the fragments of k-step i + 1 are in flight while the DMMAs of k-step i issue, no DMMA is
+// predicated); the last layer (one n-tile) is split over the warps along K, two accumulator chains
+// per warp, and summed (+ bias) by the first 64 threads of the group.
+constexpr int kUnitRows = 8;       // scenarios per lift unit = rows of one m-tile
+constexpr int kActPitch = 8;       // doubles per activation row k (A-fragment loads are conflict free)
 
-__device__ __forceinline__ void quarter_barrier(int id) {
-  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+template <int THREADS>
+__device__ __forceinline__ void group_barrier(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory");
 }
 
-template <int NT>
-__device__ __forceinline__ void encoder_kloop_q(const double* __restrict__ ap, const double* __restrict__ bp,
-                                                int kin, int ws, double (&c)[kQMaxTiles][2]) {
-#pragma unroll 2
-  for (int k0 = 0; k0 < kin; k0 += 4) {
-    const double a = ap[k0 * kQStride];
-    double b[NT];
+// NT n-tiles (stride 8 W columns) x `ksteps` k-steps; ap/bp point at this lane's first A / B
+// fragment element.  Two k-steps per iteration, double-buffered fragments; an odd k-step is peeled.
+template <int NT, int W, int MT>
+__device__ __forceinline__ void lift_kloop(const double* __restrict__ ap, const double* __restrict__ bp,
+                                           int ksteps, int ws, double (&c)[MT][2]) {
+  double a0 = ap[0], b0[NT], a1, b1[NT];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) b[j] = bp[k0 * ws + 16 * j];
+  for (int j = 0; j < NT; ++j) b0[j] = bp[8 * W * j];
+  const int pairs = ksteps >> 1, last = ksteps - 1;
+  const int astep = 4 * kActPitch, bstep = 4 * ws;
+#pragma unroll 1
+  for (int i = 0; i < pairs; ++i) {
+    const double* ap1 = ap + (2 * i + 1) * astep;
+    const double* bp1 = bp + (2 * i + 1) * bstep;
+    a1 = ap1[0];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) dmma_m8n8k4(c[j][0], c[j][1], a, b[j]);
+    for (int j = 0; j < NT; ++j) b1[j] = bp1[8 * W * j];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) dmma_m8n8k4(c[j][0], c[j][1], a0, b0[j]);
+    const int k2 = min(2 * i + 2, last);   // the very last prefetch re-loads a valid k-step
+    const double* ap2 = ap + k2 * astep;
+    const double* bp2 = bp + k2 * bstep;
+    a0 = ap2[0];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) b0[j] = bp2[8 * W * j];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) dmma_m8n8k4(c[j][0], c[j][1], a1, b1[j]);
+  }
+  if (ksteps & 1) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j) dmma_m8n8k4(c[j][0], c[j][1], a0, b0[j]);
   }
 }
 
-// in0: layer-0 input of the quarter, k-major in0[k * kQStride + row] (rows [n, inpad[0]) zero);
-// act: the quarter's activation buffer (actw * kQStride doubles); bar_id: the quarter's barrier.
-// The caller synchronises the quarter before the call; ends with a quarter barrier.
-template <typename Store>
-__device__ __forceinline__ void encoder_layers_q(const EncParams& p, const double* in0, double* act,
-                                                 const double* wsm, uint64_t* bars, int wl, int bar_id,
-                                                 Store store) {
-  const int lane = threadIdx.x & 31;
+// One unit through all layers.  in0: layer-0 input, k-major in0[k * 8 + row] (rows [n, inpad[0]) zero);
+// bufA / bufB: ping-pong activation buffers (p.actw * kActPitch >= 64 W doubles each; the split-K
+// partial sums of the last layer go to the one that layer does not read; in0 and y may live inside
+// bufB); y: 64 doubles, y[row * 8 + col] (before the subtraction of theta(0)).
+// The caller synchronises the group before the call (in0 visible, buffers free); ends with a group
+// barrier (y visible to the group, buffers free).
+template <int W>
+__device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0, double* bufA, double* bufB,
+                                          double* y, const double* wsm, uint64_t* bars, int lw, int lane,
+                                          int bar_id) {
+  constexpr int MT = (KMPC_MAX_WIDTH / 8 + W - 1) / W;   // n-tiles per warp at the widest layer
   const int gid = lane >> 2, tig = lane & 3;   // mma fragment coordinates
-  for (int l = 0; l < p.n_layers; ++l) {
-    const int kin = p.inpad[l], out = p.dims[l + 1], ws = p.wstride[l];
+  const double* src = in0;
+  double* dst = bufA;
+  const int nl = p.n_layers;
+  for (int l = 0; l + 1 < nl; ++l) {
+    const int ksteps = p.inpad[l] >> 2, out = p.dims[l + 1], ws = p.wstride[l];
     const int nt = (out + 7) >> 3;
-    const bool last = (l == p.n_layers - 1);
-    mbar_wait(&bars[l], 0);
+    mbar_wait(&bars[l], 0);   // layer l's weights have landed (returns at once after the first unit)
     const double* wt = wsm + p.woff[l];
-    const double* bias = wt + kin * ws;
-    double c[kQMaxTiles][2];
+    const double* bias = wt + p.inpad[l] * ws;
+    double c[MT][2];
 #pragma unroll
-    for (int j = 0; j < kQMaxTiles; ++j) {
-      const int tile = wl + 2 * j;
-      c[j][0] = (tile < nt) ? bias[tile * 8 + 2 * tig] : 0.0;
-      c[j][1] = (tile < nt) ? bias[tile * 8 + 2 * tig + 1] : 0.0;
+    for (int j = 0; j < MT; ++j) {
+      const int tile = lw + W * j;
+      const double2 bb = (tile < nt) ? *reinterpret_cast<const double2*>(bias + tile * 8 + 2 * tig)
+                                     : make_double2(0.0, 0.0);
+      c[j][0] = bb.x;
+      c[j][1] = bb.y;
     }
-    const double* ap = (l == 0 ? in0 : act) + tig * kQStride + gid;
-    const double* bp = wt + tig * ws + wl * 8 + gid;
-    const int my_nt = (nt > wl) ? ((nt - wl + 1) >> 1) : 0;   // warp-uniform
+    const double* ap = src + tig * kActPitch + gid;
+    const double* bp = wt + tig * ws + lw * 8 + gid;
+    const int my_nt = (nt > lw) ? ((nt - lw + W - 1) / W) : 0;   // warp-uniform
     switch (my_nt) {
-      case 8: encoder_kloop_q<8>(ap, bp, kin, ws, c); break;
-      case 7: encoder_kloop_q<7>(ap, bp, kin, ws, c); break;
-      case 6: encoder_kloop_q<6>(ap, bp, kin, ws, c); break;
-      case 5: encoder_kloop_q<5>(ap, bp, kin, ws, c); break;
-      case 4: encoder_kloop_q<4>(ap, bp, kin, ws, c); break;
-      case 3: encoder_kloop_q<3>(ap, bp, kin, ws, c); break;
-      case 2: encoder_kloop_q<2>(ap, bp, kin, ws, c); break;
-      case 1: encoder_kloop_q<1>(ap, bp, kin, ws, c); break;
+      case 8: if (MT >= 8) lift_kloop<(MT >= 8 ? 8 : 1), W, MT>(ap, bp, ksteps, ws, c); break;
+      case 7: if (MT >= 7) lift_kloop<(MT >= 7 ? 7 : 1), W, MT>(ap, bp, ksteps, ws, c); break;
+      case 6: if (MT >= 6) lift_kloop<(MT >= 6 ? 6 : 1), W, MT>(ap, bp, ksteps, ws, c); break;
+      case 5: if (MT >= 5) lift_kloop<(MT >= 5 ? 5 : 1), W, MT>(ap, bp, ksteps, ws, c); break;
+      case 4: lift_kloop<4, W, MT>(ap, bp, ksteps, ws, c); break;
+      case 3: lift_kloop<3, W, MT>(ap, bp, ksteps, ws, c); break;
+      case 2: lift_kloop<2, W, MT>(ap, bp, ksteps, ws, c); break;
+      case 1: lift_kloop<1, W, MT>(ap, bp, ksteps, ws, c); break;
       default: break;
     }
-    quarter_barrier(bar_id);   // both warps have finished reading the activations of this layer
 #pragma unroll
-    for (int j = 0; j < kQMaxTiles; ++j) {
-      const int tile = wl + 2 * j;
+    for (int j = 0; j < MT; ++j) {
+      const int tile = lw + W * j;
       if (tile < nt) {
         const int col = tile * 8 + 2 * tig;
-        if (!last) {
-          act[col * kQStride + gid] = relu_nan(c[j][0]);
-          act[(col + 1) * kQStride + gid] = relu_nan(c[j][1]);
-        } else {
-          if (col < out) store(gid, col, c[j][0]);
-          if (col + 1 < out) store(gid, col + 1, c[j][1]);
-        }
+        dst[col * kActPitch + gid] = relu_nan(c[j][0]);
+        dst[(col + 1) * kActPitch + gid] = relu_nan(c[j][1]);
       }
     }
-    quarter_barrier(bar_id);
+    group_barrier<W * 32>(bar_id);   // layer l + 1 reads what every warp has just written
+    src = dst;
+    dst = (dst == bufA) ? bufB : bufA;
+  }
+  // last layer: one n-tile (out <= 8), K split over the warps, two accumulator chains per warp
+  {
+    const int l = nl - 1;
+    const int ksteps = p.inpad[l] >> 2, out = p.dims[l + 1], ws = p.wstride[l];
+    mbar_wait(&bars[l], 0);
+    const double* wt = wsm + p.woff[l];
+    const double* bias = wt + p.inpad[l] * ws;
+    const int per = (ksteps + W - 1) / W;
+    const int kb = min(lw * per, ksteps), ke = min(kb + per, ksteps);
+    const double* ap = src + tig * kActPitch + gid;
+    const double* bp = wt + tig * ws + gid;
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll 1
+    for (int ks = kb; ks + 1 < ke; ks += 2) {
+      const double a0 = ap[ks * (4 * kActPitch)], b0 = bp[ks * 4 * ws];
+      const double a1 = ap[(ks + 1) * (4 * kActPitch)], b1 = bp[(ks + 1) * 4 * ws];
+      dmma_m8n8k4(c0, c1, a0, b0);
+      dmma_m8n8k4(d0, d1, a1, b1);
+    }
+    if ((ke - kb) & 1) dmma_m8n8k4(c0, c1, ap[(ke - 1) * (4 * kActPitch)], bp[(ke - 1) * 4 * ws]);
+    double* part = dst;
+    *reinterpret_cast<double2*>(part + lw * 64 + gid * 8 + 2 * tig) = make_double2(c0 + d0, c1 + d1);
+    group_barrier<W * 32>(bar_id);
+    const int t = lw * 32 + lane;
+    if (t < 64) {
+      const int col = t & 7;
+      double s = part[t];
+#pragma unroll
+      for (int w = 1; w < W; ++w) s += part[w * 64 + t];
+      y[t] = (col < out) ? s + bias[col] : 0.0;
+    }
+    group_barrier<W * 32>(bar_id);
   }
 }
 #endif  // __CUDACC__

@@ -31,6 +31,8 @@
 
 namespace kmpc {
 
+__device__ __forceinline__ void quarter_barrier(int id) { group_barrier<64>(id); }
+
 constexpr int FG = 8;            // lanes per scenario
 constexpr int FNZ = 8;           // lifted dimension
 constexpr int FN = 10;           // horizon
@@ -46,9 +48,11 @@ constexpr int oHF = 112;         // 72 doubles: 2H packed lower triangle (55), f
 constexpr int oL = 0;            // 60: strictly-lower factor + forward-substituted rhs, column major
 constexpr int oXS = 60;          // 10: current iterate x
 constexpr int oGS = 70;          // 10: gradient 2 H x + f
-constexpr int kZbuf = kTileS * FNZ;    // lift outputs of the tile (per quarter: 64 doubles, whose first
-                                       // 48 double as the quarter's layer-0 input block)
-static_assert(4 * kQStride <= kQRows * FNZ, "layer-0 input block aliases the quarter's lift outputs");
+// unit region (one per quarter = 8 scenarios): [ bufA | bufB ] ping-pong activations of the unit's
+// lift, aliased by the unit's scratch (8 x kScr doubles from the start: the scratch is dead while the
+// unit lifts); the tail beyond the scratch holds the layer-0 input block (4 x 8) and the lift outputs
+// (8 x 8); the split-K partials of the last layer use the ping-pong buffer that layer does not read
+constexpr int kIn0 = 4 * kUnitRows, kYout = kUnitRows * FNZ;
 
 // The identity-output build emits the 55 + 10 reduced values diagonal by diagonal (running sums
 // along a diagonal); this table maps emission number -> position in HF (packed lower triangle
@@ -67,14 +71,21 @@ __host__ __device__ constexpr int lcol(int j) {
 }
 
 struct FusedSmem {  // offsets in doubles from the start of dynamic shared memory
-  int scratch, zbuf, wsm, bars, total_bytes;
+  int region;       // doubles per unit region (4 regions from offset 0)
+  int actbuf;       // doubles per ping-pong buffer
+  int in0, yout;    // offsets of the layer-0 input block / lift outputs inside a region
+  int wsm, bars, total_bytes;
 };
 inline FusedSmem fused_smem_layout(const EncParams* p) {
   FusedSmem L;
-  L.scratch = 0;                 // 32 x kScr; quarter q's activations alias scenarios 8q .. 8q+7
-  L.zbuf = kTileS * kScr;
-  L.wsm = L.zbuf + kZbuf;
-  L.wsm = (L.wsm + 1) & ~1;
+  L.actbuf = p ? p->actw * kActPitch : 0;
+  const int scratch = kUnitRows * kScr;
+  L.in0 = scratch;
+  L.yout = scratch + kIn0;
+  L.region = scratch + kIn0 + kYout;
+  if (2 * L.actbuf > L.region) L.region = 2 * L.actbuf;
+  L.region = (L.region + 1) & ~1;
+  L.wsm = 4 * L.region;
   L.bars = L.wsm + (p ? p->total_w : 0);
   L.bars = (L.bars + 1) & ~1;
   L.total_bytes = (L.bars + KMPC_MAX_LAYERS) * 8;
@@ -395,12 +406,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.sm.bars);
   const int tid = threadIdx.x;
   const int sc = tid >> 3, l = tid & 7;
-  double* scr = smem + a.sm.scratch + sc * kScr;
-  // quarter = 2 warps = 8 scenarios: its own activation buffer (aliasing its scenarios' scratch),
-  // lift outputs and named barrier; quarters never wait for each other inside the step loop
+  // quarter = 2 warps = 8 scenarios = one lift unit: its own region (ping-pong activations aliasing
+  // its scenarios' scratch, layer-0 block, lift outputs) and named barrier; quarters never wait for
+  // each other inside the step loop
   const int quarter = tid >> 6, wl = (tid >> 5) & 1, qbar = 1 + quarter;
-  double* qact = smem + a.sm.scratch + quarter * (kQRows * kScr);
-  double* qz = smem + a.sm.zbuf + quarter * (kQRows * FNZ);
+  double* region = smem + quarter * a.sm.region;
+  double* scr = region + (sc & 7) * kScr;
+  double* in0 = region + a.sm.in0;
+  double* yout = region + a.sm.yout;
   double* red = scr + oRED;
   double* ex = scr + oEX;
   double* HF = scr + oHF;
@@ -664,16 +677,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
       // ================= lift(x+) =================
       double yl;
       if (MLP) {
-        // both warps of the quarter are past their last read of qz (the previous lift) and of the
-        // scratch their activations are about to overwrite
-        quarter_barrier(qbar);
-        if (l < 4) qz[l * kQStride + (sc & 7)] = (l == 0) ? x1n : ((l == 1) ? x2n : 0.0);
+        // x+ -> the unit's layer-0 block (k-major); the barrier also says that both warps of the unit
+        // are done with the scratch their activations are about to overwrite
+        if (l < 4) in0[l * kUnitRows + (sc & 7)] = (l == 0) ? x1n : ((l == 1) ? x2n : 0.0);
         quarter_barrier(qbar);
         if (TIMED) tq += clock64() - c0, c0 = clock64();
         if (!(a.dbg_skip & 2))
-          encoder_layers_q(a.p, qz, qact, wsm, bars, wl, qbar,
-                           [&](int r, int col, double v) { qz[r * FNZ + col] = v; });
-        yl = qz[(sc & 7) * FNZ + l];
+          lift_unit<2>(a.p, in0, region, region + a.sm.actbuf, yout, wsm, bars, wl, tid & 31, qbar);
+        yl = yout[(sc & 7) * FNZ + l];
         if (c.lift_mode != KMPC_LIFT_RAW) yl -= a.p.z0[l];
         if (TIMED) tl += clock64() - c0, c0 = clock64();
       } else {
@@ -816,7 +827,6 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
         }
       }
     }
-    quarter_barrier(qbar);  // the next tile reuses the quarter's scratch / lift outputs
   }
   if (TIMED && tid == 0) {
     a.timing[blockIdx.x * 4 + 0] = tq;
@@ -854,7 +864,7 @@ bool fused_eligible(const kmpc_loop_config& c, const kmpc_encoder* enc) {
     if (!enc || enc->smem_bytes <= 0) return false;
     if (c.lift_mode == KMPC_LIFT_STACK) return false;
     if (enc->p.dims[0] != 2 || enc->p.dims[enc->p.n_layers] != FNZ) return false;
-    if (enc->p.actw * kQStride > kQRows * kScr) return false;   // a quarter's activations alias its scratch
+    if (enc->p.actw * kActPitch < 128) return false;            // split-K partials live in a ping-pong buffer
     const FusedSmem L = fused_smem_layout(&enc->p);
     if (L.total_bytes > enc->max_smem_optin) return false;
   } else if (c.lift_kind != KMPC_LIFTKIND_RBF) {

@@ -235,7 +235,7 @@ int kmpc_encoder_create(kmpc_encoder** out, const double* const* W, const double
     const int in = dims[l], o = dims[l + 1], op = enc->p.pad[l + 1];
     const int inpad = (in + 3) & ~3, o8 = (o + 7) & ~7;
     int wsd = (o + 3) & ~3;
-    while ((wsd & 15) != 4) wsd += 4;
+    while ((wsd & 7) != 4) wsd += 4;   // == 4 or 12 (mod 16): both conflict free
     enc->p.inpad[l] = inpad;
     enc->p.wstride[l] = wsd;
     enc->p.woff[l] = (int)packed.size();
