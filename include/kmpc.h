@@ -215,6 +215,31 @@ int kmpc_ctx_is_fused(const kmpc_ctx* ctx);
  * scaled to the event-timed launch on the fused path */
 int kmpc_closed_loop_steps_timed(kmpc_ctx* ctx, int T, void* stream, float* ms);
 
+/* ------------------------------------------------------------------ snapshot generator -------
+ * data_generate.py:17-74 (duffing_generate) / 82-152 (vanderpol_generate): n_traj trajectories,
+ * n_step vectorised RK4 steps (h = 0.05, zero-order-hold input), outputs re-ordered trajectory-major
+ * (l.63-74) -- snapshot-major here: X, Y (M, n = 2), U (M), M = n_traj * n_step, snapshot
+ * traj * n_step + j = step j of trajectory traj.  The random draws stay with the caller
+ * (reference: u0 = 4 rand(N, N_Traj) - 2 then x0 = 4 rand(n, N_Traj) - 2 from numpy's global
+ * stream): x0 [dev] (n_traj, 2), u0 [dev] (n_step, n_traj) in the reference's own layout;
+ * params [dev] (5) as for kmpc_plant_step.                                                        */
+int kmpc_generate_snapshots(const double* x0, const double* u0, const double* params, int plant_kind,
+                            int rk4_variant, double h, int64_t n_traj, int n_step, double* X, double* Y,
+                            double* U, void* stream);
+
+/* ------------------------------------------------------------------ open-loop predictor ------
+ * duffing.py:290-343 / vanderpol.py:292-348: along T consecutive snapshots of each of n_seq
+ * sequences (sequence s starts at snapshot s * seq_stride; the reference checks one: n_seq = 1,
+ * T = plotTime) the lifted state restarts from the TRUE lifted state psi every reset_every (10)
+ * steps and follows z+ = A z + B u in between; logged BEFORE the propagation: decoder_X (n_seq,T,nz)
+ * = z and test_Y (n_seq,T,n) = C z.  psi [dev] (M, nz) = lift of the snapshots (kmpc_encode /
+ * kmpc_rbf_lift), x [dev] (M, n), u [dev] (M).  rmse (nullable, [dev] (n_seq)):
+ * || (test_Y[:, rmse_row] - x[:T, rmse_row]) / T ||_2 (duffing.py:341 row 0, vanderpol.py:346 row 1). */
+int kmpc_open_loop_predict(const double* psi, const double* x, const double* u, const double* A,
+                           const double* B, const double* C, int nz, int n, int64_t n_seq, int T,
+                           int64_t seq_stride, int reset_every, int rmse_row, double* decoder_X,
+                           double* test_Y, double* rmse, void* stream);
+
 /* ------------------------------------------------------------------ roofline denominators ----
  * MEASURED_PEAKS.json carries no fp64 number: measure this GPU's fp64 tensor-path
  * (mma.sync.m8n8k4.f64) and CUDA-core (DFMA) peaks, TFLOP/s, ~25 ms each; synchronises. */

@@ -83,12 +83,34 @@ _np.savez(_OUT,
     maxStep=maxStep)
 '''
 
+EPILOGUE_PRED = r'''
+import numpy as _np
+def _n(v):
+    try:
+        return v.detach().numpy()
+    except AttributeError:
+        return _np.asarray(v)
+# test snapshot set of the open-loop check (np.random.seed(33 / 50) + data_generate) and the
+# predictor outputs of duffing.py:272-343 / vanderpol.py:272-348
+_np.savez(_OUT,
+    A=_n(A), B=_n(B), C=_n(C),
+    X_head=_n(X)[:, :600], Y_head=_n(Y)[:, :600], U_head=_n(U)[:, :600],
+    X_sum=_n(X).sum(axis=1), Y_sum=_n(Y).sum(axis=1), U_sum=_n(U).sum(axis=1),
+    X_tail=_n(X)[:, -300:], Y_tail=_n(Y)[:, -300:], U_tail=_n(U)[:, -300:],
+    n_snap=_n(X).shape[1],
+    test_Y=_n(test_Y), decoder_X=_n(decoder_X), marker_X=_n(marker_X), test_X=_n(test_X),
+    RMSE=_np.asarray(RMSE), plotTime=plotTime)
+'''
+
 JOBS = {
     # name: (script, truncate-after-line (1-based, inclusive), steps, epilogue, needed files)
     "duffing": ("duffing.py", 1013, 300, EPILOGUE_ENC, ["AutoEncoder_20220418_duffing_2.pkl"]),
     "vanderpol": ("vanderpol.py", 952, 400, EPILOGUE_ENC, ["AutoEncoder_20220414_4.pkl"]),
     "duffing_rbf": ("duffing_RBF.py", 527, 120, EPILOGUE_RBF, []),
     "vanderpol_rbf": ("vanderpol_RBF.py", 527, 120, EPILOGUE_RBF, []),
+    # open-loop multi-step predictor + its test snapshot set (no closed loop: steps = None)
+    "duffing_predict": ("duffing.py", 343, None, EPILOGUE_PRED, ["AutoEncoder_20220418_duffing_2.pkl"]),
+    "vanderpol_predict": ("vanderpol.py", 348, None, EPILOGUE_PRED, ["AutoEncoder_20220414_4.pkl"]),
 }
 
 
@@ -103,8 +125,9 @@ def run_script(name):
             lines = fh.read().split("\n")[:cut]
         text = "\n".join(lines)
         text = text.replace("+ u])", "+ np.ravel(u)])")
-        text, nsub = re.subn(r"^maxStep = 10000$", "maxStep = %d" % steps, text, flags=re.M)
-        assert nsub == 1, "maxStep patch point not found"
+        if steps is not None:
+            text, nsub = re.subn(r"^maxStep = 10000$", "maxStep = %d" % steps, text, flags=re.M)
+            assert nsub == 1, "maxStep patch point not found"
         out = os.path.join(HERE, "ref_%s.npz" % name)
         body = PROLOGUE + text + "\n_OUT = %r\n" % out + epilogue
         path = os.path.join(work, "run_" + script)
@@ -166,7 +189,8 @@ def export_vdp_mat():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="weights,vdp_mat,duffing,vanderpol,duffing_rbf,vanderpol_rbf")
+    ap.add_argument("--only", default="weights,vdp_mat,duffing,vanderpol,duffing_rbf,vanderpol_rbf,"
+                                       "duffing_predict,vanderpol_predict")
     args = ap.parse_args()
     for name in args.only.split(","):
         if name == "weights":

@@ -471,3 +471,82 @@ def test_full_size_rbf_horizon50_properties():
     o = ocl.run_loop(cfg, g["A"], g["B"], g["C"], x0[0], T, update=ocl.UPDATE_RLS, qp="exact",
                      warm=orls.RLSState.warm(G, Aq, XV[:, :8], G[:8, :8]))
     assert np.abs(o["X"] - lx[:, 0]).max() < 1e-7
+
+
+# ------------------------------------------- snapshot generator + open-loop predictor (N1, N2) --
+@pytest.mark.parametrize("name,seed", [("duffing", 33), ("vanderpol", 50)])
+def test_snapshot_generator_matches_oracle_and_reference_run(name, seed):
+    """kmpc_generate_snapshots through the reference's call shape (data_generate.generate)."""
+    from koopman_online_updated_mpc_b200 import data_generate as DG
+    g = H.golden("ref_%s_predict.npz" % name)
+    np.random.seed(seed)
+    gen = DG.generate(100, 100)
+    X, Y, U = gen.duffing_generate() if name == "duffing" else gen.vanderpol_generate()
+    assert X.shape == (2, 10000) and Y.shape == (2, 10000) and U.shape == (1, 10000)
+    np.testing.assert_allclose(X[:, :600], g["X_head"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(Y[:, :600], g["Y_head"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(X[:, -300:], g["X_tail"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(U[:, -300:], g["U_tail"], rtol=0, atol=0)
+    p = oplant.DUFFING_PRE if name == "duffing" else oplant.VDP_PRE
+    Xo, Yo, Uo = oplant.generate_snapshots(100, 100, p, np.random.RandomState(seed))
+    np.testing.assert_allclose(X, Xo, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(Y, Yo, rtol=0, atol=1e-12)
+    assert np.array_equal(U, Uo)
+
+
+def test_snapshot_generator_ragged_shapes_and_variants():
+    from koopman_online_updated_mpc_b200 import data_generate as DG
+    rs = np.random.RandomState(3)
+    for n_traj, n_step in ((1, 1), (127, 7), (129, 8), (300, 19), (5, 100)):   # ragged tiles / chunks
+        x0 = rs.uniform(-1.5, 1.5, (n_traj, 2))
+        u0 = rs.uniform(-2, 2, (n_step, n_traj))
+        for variant in (oplant.RK4_PYTHON, oplant.RK4_MATLAB):
+            X, Y, U = DG.generate_snapshots(x0, u0, oplant.VDP_PRE, rk4_variant=variant)
+            x, Xs, Ys = x0.copy(), [], []
+            for j in range(n_step):
+                xn = oplant.rk4_step(x, u0[j], np.asarray(oplant.VDP_PRE), variant=variant)
+                Xs.append(x)
+                Ys.append(xn)
+                x = xn
+            np.testing.assert_allclose(X.cpu().numpy(), np.stack(Xs, 1).reshape(-1, 2), rtol=0, atol=1e-12)
+            np.testing.assert_allclose(Y.cpu().numpy(), np.stack(Ys, 1).reshape(-1, 2), rtol=0, atol=1e-12)
+            assert np.array_equal(U.cpu().numpy(), u0.T.reshape(-1))
+    x0 = np.abs(rs.uniform(0, 2, (40, 2)))        # tank map (Tank_System.m:9-10, clamp at 0)
+    u0 = rs.uniform(-1, 3, (30, 40))
+    X, Y, U = DG.generate_snapshots(x0, u0, oplant.TANK_PRE, kind=oplant.PLANT_TANK)
+    x = x0.copy()
+    for j in range(30):
+        xn = oplant.tank_step(x, u0[j], np.asarray(oplant.TANK_PRE))
+        np.testing.assert_allclose(Y.cpu().numpy().reshape(40, 30, 2)[:, j], xn, rtol=0, atol=1e-12)
+        x = xn
+    Xe, Ye, Ue = DG.generate_snapshots(np.zeros((0, 2)), np.zeros((5, 0)), oplant.VDP_PRE)   # empty set
+    assert Xe.shape == (0, 2) and Ue.shape == (0,)
+
+
+@pytest.mark.parametrize("name,wsys,row", [("duffing", "duffing", 0), ("vanderpol", "vdp", 1)])
+def test_open_loop_predictor_matches_reference_run(name, wsys, row):
+    """kmpc_open_loop_predict against the reference's own predictor outputs and RMSE
+    (duffing.py:290-343 / vanderpol.py:292-348) and the oracle on many sequences."""
+    from koopman_online_updated_mpc_b200 import predict as P
+    from oracle import predict as opredict
+    g = H.golden("ref_%s_predict.npz" % name)
+    Ws, bs = H.oracle_weights(wsys)
+    enc = K.Encoder(Ws, bs)
+    T = int(g["plotTime"])
+    X, U = g["X_head"], g["U_head"]
+    PHIX = enc(X.T.copy()).T
+    tY, dX, rmse = P.open_loop_predict(PHIX, X, U, g["A"], g["B"], g["C"], T, rmse_row=row)
+    np.testing.assert_allclose(tY, g["test_Y"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(dX, g["decoder_X"], rtol=0, atol=1e-11)
+    assert abs(rmse - float(g["RMSE"])) < 1e-13
+    # many sequences, ragged last segment (T not a multiple of reset_every), other reset period
+    T2, stride, nseq = 37, 50, 12
+    tYs, dXs, rm = P.open_loop_predict(PHIX, X, U, g["A"], g["B"], g["C"], T2, reset_every=7, rmse_row=row,
+                                       n_seq=nseq, seq_stride=stride)
+    for s in range(nseq):
+        Xs, Us = X[:, s * stride:], U[:, s * stride:]
+        oY, oD, _ = opredict.open_loop_predict(lambda x: olift.lift_mlp(Ws, bs, x), g["A"], g["B"], g["C"], Xs, Us, T2,
+                                               reset_every=7)
+        np.testing.assert_allclose(tYs[s], oY, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(dXs[s], oD, rtol=0, atol=1e-11)
+        assert abs(rm[s] - opredict.rmse(oY, Xs, T2, row)) < 1e-13

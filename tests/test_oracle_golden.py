@@ -198,3 +198,26 @@ def test_tank_restatement_behaves_like_the_paper():
     x2 = out["X"][:, 1]
     assert abs(x2[95] - 1.0) < 5e-3 and x2[100:130].min() < 0.9 and abs(x2[255] - 1.0) < 5e-3
     assert np.all(np.abs(np.diff(np.concatenate([[0.0], out["U"]]))) <= 0.5 + 1e-9)  # dU box
+
+
+# ------------------------------------------------ snapshot generator + open-loop predictor (N1, N2) --
+@pytest.mark.parametrize("name,wsys,row,seed", [("duffing", "duffing", 0, 33), ("vanderpol", "vdp", 1, 50)])
+def test_generator_and_open_loop_predictor_match_reference_run(name, wsys, row, seed):
+    """oracle/plant.generate_snapshots and oracle/predict.py against the reference's own run of
+    data_generate.py + duffing.py:262-343 / vanderpol.py:263-348 (ref_*_predict.npz)."""
+    from oracle import lift as olift, plant as oplant, predict as opredict
+    g = H.golden("ref_%s_predict.npz" % name)
+    Ws, bs = H.oracle_weights(wsys)
+    p = oplant.DUFFING_PRE if name == "duffing" else oplant.VDP_PRE
+    X, Y, U = oplant.generate_snapshots(100, 100, p, np.random.RandomState(seed))
+    assert X.shape[1] == int(g["n_snap"])
+    np.testing.assert_allclose(X[:, :600], g["X_head"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(Y[:, -300:], g["Y_tail"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(U[:, :600], g["U_head"], rtol=0, atol=0)
+    np.testing.assert_allclose(X.sum(axis=1), g["X_sum"], rtol=0, atol=1e-10)
+    T = int(g["plotTime"])
+    tY, dX, mX = opredict.open_loop_predict(lambda x: olift.lift_mlp(Ws, bs, x), g["A"], g["B"], g["C"], X, U, T)
+    np.testing.assert_allclose(tY, g["test_Y"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(dX, g["decoder_X"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(mX, g["marker_X"], rtol=0, atol=1e-12)
+    assert abs(opredict.rmse(tY, X, T, row) - float(g["RMSE"])) < 1e-14
