@@ -89,6 +89,12 @@ int kmpc_gram_accumulate(const double* psi, const double* psi_next, const double
 int kmpc_gram_from_snapshots(const kmpc_encoder* enc, int lift_mode, const double* x,
                              const double* y, const double* u, int64_t M, double* pack,
                              void* stream);
+/* trajectory-aware variant for CONSECUTIVE trajectory-major snapshots (data_generate.py:63-74 /
+ * kmpc_generate_snapshots: y of snapshot j is x of snapshot j + 1 of the same trajectory): one
+ * encode per state (n_step + 1 per trajectory) instead of two per snapshot; same pack.          */
+int kmpc_gram_from_trajectories(const kmpc_encoder* enc, int lift_mode, const double* x,
+                                const double* y, const double* u, int64_t n_traj, int n_step,
+                                double* pack, void* stream);
 #define KMPC_C_PYTHON 0 /* C = (X PHIX')(PHIX PHIX')^-1            duffing.py:177        */
 #define KMPC_C_JOINT 1  /* C = block of [PHIY;X] V' (V V')^-1      Tank_System.m:96-100  */
 /* A [dev] (nz,nz), B [dev] (nz,1), C [dev] (n,nz), status [dev] (1) */

@@ -42,6 +42,7 @@ _PROTOS = {
     "kmpc_gram_pack_len": (_i64, [_i, _i]),
     "kmpc_gram_accumulate": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp]),
     "kmpc_gram_from_snapshots": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "kmpc_gram_from_trajectories": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "kmpc_edmd_solve": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "kmpc_rls_update": (_i, [_vp] * 11 + [_i64, _i, _i, _d, _i, _vp]),
     "kmpc_qp_first_move": (_i, [_vp] * 8 + [_d, _d, _i, _i, _i, _i64, _i, _vp, _vp, _vp, _i, _d, _vp]),

@@ -18,12 +18,13 @@ bool fused_eligible(const kmpc_loop_config& c, const kmpc_encoder* enc);
 int fused_launch(const LoopDev& d, const kmpc_encoder* enc, int64_t step0, int T, int first,
                  long long* timing, int* grid_out, cudaStream_t st);
 
-constexpr int kLoopThreads = 128;
+constexpr int kLoopThreads = 128;      // default block
+constexpr int kLoopThreadsMax = 256;   // large QP workspaces: one bigger block per SM (see select_launch)
 
 // G lanes per scenario; NZ/N/OUT/DU > 0 give a compile-time QP shape (loops unrolled, indices
 // folded), NZ == 0 reads the shape from the config at run time.
 template <int G, int NZ, int N, int OUT, int DU, bool FAST = true>
-__global__ void __launch_bounds__(kLoopThreads)
+__global__ void __launch_bounds__(kLoopThreadsMax)
 loop_qp_plant_kernel(LoopDev d, int64_t step, int64_t log_slot) {
   extern __shared__ double smem[];
   pdl_wait();  // everything this kernel reads (A, B, C, z, x) comes from the previous kernels
@@ -103,11 +104,19 @@ static bool select_launch(const kmpc_loop_config& c, LoopLaunch* L) {
   const int rls_ws = rls_ws_doubles(c.nz, 2) * (int)sizeof(double);
   L->qp_spb = kLoopThreads / L->qp_g;
   while (L->qp_spb > 1 && L->qp_spb * qp_ws > budget) L->qp_spb >>= 1;
+  // a workspace so large that two default blocks do not fit an SM (N = 50: 32 KB per scenario): one
+  // block with as many scenarios as the SM's shared memory holds instead (7 warps instead of 4)
+  const int sm_smem = 225 * 1024;
+  if (2 * (L->qp_spb * qp_ws + 1024) > sm_smem) {
+    int spb = sm_smem / qp_ws;
+    if (spb > kLoopThreadsMax / L->qp_g) spb = kLoopThreadsMax / L->qp_g;
+    if (spb > L->qp_spb) L->qp_spb = spb;
+  }
   L->rls_spb = kLoopThreads / L->rls_g;
   while (L->rls_spb > 1 && L->rls_spb * rls_ws > budget) L->rls_spb >>= 1;
   L->qp_smem = L->qp_spb * qp_ws;
   L->rls_smem = L->rls_spb * rls_ws;
-  return L->qp_smem <= budget && L->rls_smem <= budget;
+  return L->qp_smem <= sm_smem && L->rls_smem <= budget;
 }
 
 }  // namespace kmpc
@@ -162,6 +171,7 @@ int kmpc_ctx_create(kmpc_ctx** out, const kmpc_loop_config* cfg, const kmpc_loop
   ctx->d.x_prev = nullptr;
   ctx->d_timing = nullptr;
   ctx->d.wset = nullptr;
+  ctx->d.qp_x = nullptr;
   ctx->fused = fused_eligible(ctx->d.c, enc);
   if (cudaMalloc(&ctx->d.z_next, (size_t)c.S * c.nz * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&ctx->d.x_prev, (size_t)c.S * c.n * sizeof(double)) != cudaSuccess) {
@@ -172,6 +182,18 @@ int kmpc_ctx_create(kmpc_ctx** out, const kmpc_loop_config* cfg, const kmpc_loop
                      cudaMemsetAsync(ctx->d.wset, 0, (size_t)c.S * 2 * sizeof(unsigned int), as_stream(stream)) != cudaSuccess)) {
     kmpc_ctx_destroy(ctx);
     return KMPC_ERR_ALLOC;
+  }
+  {
+    // generic kernels: warm start from the previous step's optimal moves (0xFF bytes = NaN = none
+    // yet).  Debug knob: KMPC_QP_WARM=0 cold-starts every QP.
+    const char* e = getenv("KMPC_QP_WARM");
+    if (!ctx->fused && !(e && e[0] == '0')) {
+      if (cudaMalloc(&ctx->d.qp_x, (size_t)c.S * c.N * sizeof(double)) != cudaSuccess ||
+          cudaMemsetAsync(ctx->d.qp_x, 0xFF, (size_t)c.S * c.N * sizeof(double), as_stream(stream)) != cudaSuccess) {
+        kmpc_ctx_destroy(ctx);
+        return KMPC_ERR_ALLOC;
+      }
+    }
   }
   if (!select_launch(c, &ctx->launch)) {
     kmpc_ctx_destroy(ctx);
@@ -193,6 +215,7 @@ int kmpc_ctx_destroy(kmpc_ctx* ctx) {
   if (ctx->d.x_prev) cudaFree(ctx->d.x_prev);
   if (ctx->d_timing) cudaFree(ctx->d_timing);
   if (ctx->d.wset) cudaFree(ctx->d.wset);
+  if (ctx->d.qp_x) cudaFree(ctx->d.qp_x);
   delete ctx;
   return KMPC_OK;
 }
@@ -207,6 +230,8 @@ int kmpc_ctx_reset(kmpc_ctx* ctx, int rls_started, void* stream) {
   ctx->rls_started = rls_started;
   if (ctx->d.wset)
     KMPC_CUDA(cudaMemsetAsync(ctx->d.wset, 0, (size_t)ctx->d.c.S * 2 * sizeof(unsigned int), as_stream(stream)));
+  if (ctx->d.qp_x)
+    KMPC_CUDA(cudaMemsetAsync(ctx->d.qp_x, 0xFF, (size_t)ctx->d.c.S * ctx->d.c.N * sizeof(double), as_stream(stream)));
   return KMPC_OK;
 }
 

@@ -18,7 +18,7 @@ template <int NZ, int NX>
 __global__ void __launch_bounds__(64 * ((NZ + 1 + 2) / 3))
 gram_kernel(const double* __restrict__ psi, const double* __restrict__ psin,
             const double* __restrict__ u, const double* __restrict__ x, int64_t M,
-            double* __restrict__ pack) {
+            double* __restrict__ pack, int seg) {
   constexpr int NV = NZ + 1, NR = NV + NZ + NX, CB = 3, ROLES = (NV + CB - 1) / CB;
   __shared__ double red[ROLES][NR * CB];
   const int role = threadIdx.x / 64, tl = threadIdx.x % 64;
@@ -31,12 +31,17 @@ gram_kernel(const double* __restrict__ psi, const double* __restrict__ psin,
   for (int64_t m = (int64_t)blockIdx.x * 64 + tl; m < M; m += (int64_t)gridDim.x * 64) {
     double row[NR];
     static_assert(NZ % 2 == 0, "vectorised loads need even NZ");
+    // seg > 0: trajectory layout -- the lifted rows of a trajectory of `seg` snapshots are its
+    // seg + 1 consecutive states, so snapshot m reads rows m + m / seg and the one after it
+    const int64_t pr = seg ? m + m / seg : m;
+    const double* prow = psi + pr * NZ;
+    const double* nrow = seg ? prow + NZ : psin + m * NZ;
 #pragma unroll
     for (int k = 0; k < NZ; k += 2) {
-      const double2 a = __ldg(reinterpret_cast<const double2*>(psi + m * NZ + k));
+      const double2 a = __ldg(reinterpret_cast<const double2*>(prow + k));
       row[k] = a.x;
       row[k + 1] = a.y;
-      const double2 b = __ldg(reinterpret_cast<const double2*>(psin + m * NZ + k));
+      const double2 b = __ldg(reinterpret_cast<const double2*>(nrow + k));
       row[NV + k] = b.x;
       row[NV + k + 1] = b.y;
     }
@@ -47,7 +52,7 @@ gram_kernel(const double* __restrict__ psi, const double* __restrict__ psin,
 #pragma unroll
     for (int c = 0; c < CB; ++c) {
       const int col = c0 + c;
-      vc[c] = col < NZ ? __ldg(psi + m * NZ + col) : (col == NZ ? row[NZ] : 0.0);
+      vc[c] = col < NZ ? __ldg(prow + col) : (col == NZ ? row[NZ] : 0.0);
     }
 #pragma unroll
     for (int r = 0; r < NR; ++r)
@@ -87,18 +92,20 @@ gram_kernel(const double* __restrict__ psi, const double* __restrict__ psin,
 // snapshots; used for dimensions without a specialised instantiation.
 __global__ void gram_generic_kernel(const double* __restrict__ psi, const double* __restrict__ psin,
                                     const double* __restrict__ u, const double* __restrict__ x,
-                                    int64_t M, int nz, int n, double* __restrict__ pack) {
+                                    int64_t M, int nz, int n, double* __restrict__ pack, int seg) {
   const int nv = nz + 1, nr = nv + nz + n;
   const int e = threadIdx.x;
   if (e >= nr * nv) return;
   const int r = e / nv, c = e - r * nv;
   double acc = 0.0;
   for (int64_t m = blockIdx.x; m < M; m += gridDim.x) {
-    const double vc = (c < nz) ? psi[m * nz + c] : u[m];
+    const int64_t pr = seg ? m + m / seg : m;
+    const double* nrow = seg ? psi + (pr + 1) * nz : psin + m * nz;
+    const double vc = (c < nz) ? psi[pr * nz + c] : u[m];
     double vr;
-    if (r < nz) vr = psi[m * nz + r];
+    if (r < nz) vr = psi[pr * nz + r];
     else if (r == nz) vr = u[m];
-    else if (r < nv + nz) vr = psin[m * nz + (r - nv)];
+    else if (r < nv + nz) vr = nrow[r - nv];
     else vr = x[m * n + (r - nv - nz)];
     acc = fma(vr, vc, acc);
   }
@@ -147,11 +154,16 @@ int64_t kmpc_gram_pack_len(int nz, int n) {
   return (int64_t)(nv + nz + n) * nv + 1;
 }
 
-int kmpc_gram_accumulate(const double* psi, const double* psi_next, const double* u,
-                         const double* x, int64_t M, int nz, int n, double* pack, void* stream) {
-  if (nz < 1 || nz > KMPC_MAX_NZ || n < 1 || n > 4 || M < 0) return KMPC_ERR_ARG;
+}  // extern "C"
+
+namespace kmpc {
+// seg == 0: psi / psi_next are (M, nz); seg > 0: psi holds M / seg trajectories of seg + 1 lifted
+// states each and psi_next is ignored (lift.cu: kmpc_gram_from_trajectories)
+int gram_accumulate_impl(const double* psi, const double* psi_next, const double* u, const double* x,
+                         int64_t M, int nz, int n, double* pack, int seg, void* stream) {
+  if (nz < 1 || nz > KMPC_MAX_NZ || n < 1 || n > 4 || M < 0 || seg < 0) return KMPC_ERR_ARG;
   if (M == 0) return KMPC_OK;
-  if (!psi || !psi_next || !u || !x || !pack) return KMPC_ERR_ARG;
+  if (!psi || (!psi_next && !seg) || !u || !x || !pack) return KMPC_ERR_ARG;
   cudaStream_t st = as_stream(stream);
   int dev = 0, sms = 148;
   KMPC_CUDA(cudaGetDevice(&dev));
@@ -159,18 +171,26 @@ int kmpc_gram_accumulate(const double* psi, const double* psi_next, const double
   int64_t want = (M + 63) / 64;
   const unsigned grid = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
   if (nz == 8 && n == 2) {
-    gram_kernel<8, 2><<<grid, 64 * 3, 0, st>>>(psi, psi_next, u, x, M, pack);
+    gram_kernel<8, 2><<<grid, 64 * 3, 0, st>>>(psi, psi_next, u, x, M, pack, seg);
   } else if (nz == 10 && n == 2) {
-    gram_kernel<10, 2><<<grid, 64 * 4, 0, st>>>(psi, psi_next, u, x, M, pack);
+    gram_kernel<10, 2><<<grid, 64 * 4, 0, st>>>(psi, psi_next, u, x, M, pack, seg);
   } else {
     const int nv = nz + 1, outs = (nv + nz + n) * nv;
     const unsigned g2 = (unsigned)(M < (int64_t)sms * 4 ? M : (int64_t)sms * 4);
-    gram_generic_kernel<<<g2, (outs + 31) / 32 * 32, 0, st>>>(psi, psi_next, u, x, M, nz, n, pack);
+    gram_generic_kernel<<<g2, (outs + 31) / 32 * 32, 0, st>>>(psi, psi_next, u, x, M, nz, n, pack, seg);
   }
   KMPC_AFTER_LAUNCH();
   gram_count_kernel<<<1, 1, 0, st>>>(pack, (int)kmpc_gram_pack_len(nz, n) - 1, (double)M);
   KMPC_AFTER_LAUNCH();
   return KMPC_OK;
+}
+}  // namespace kmpc
+
+extern "C" {
+
+int kmpc_gram_accumulate(const double* psi, const double* psi_next, const double* u,
+                         const double* x, int64_t M, int nz, int n, double* pack, void* stream) {
+  return gram_accumulate_impl(psi, psi_next, u, x, M, nz, n, pack, 0, stream);
 }
 
 int kmpc_edmd_solve(const double* pack, int nz, int n, int c_variant, double* A, double* B,

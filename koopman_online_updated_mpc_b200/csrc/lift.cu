@@ -183,6 +183,23 @@ encoder_kernel(EncParams p, const double* __restrict__ x, double* __restrict__ z
 
 }  // namespace kmpc
 
+namespace kmpc {
+int gram_accumulate_impl(const double* psi, const double* psi_next, const double* u, const double* x,
+                         int64_t M, int nz, int n, double* pack, int seg, void* stream);   // edmd.cu
+
+// rows of a chunk of trajectories for the trajectory-aware Gram: trajectory t contributes its
+// n_step snapshot states x and the successor y of its last snapshot, n_step + 1 consecutive rows
+__global__ void traj_rows_kernel(const double* __restrict__ x, const double* __restrict__ y, int n,
+                                 int64_t n_traj, int n_step, double* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_traj * (n_step + 1)) return;
+  const int64_t t = r / (n_step + 1);
+  const int j = (int)(r - t * (n_step + 1));
+  const double* src = (j < n_step) ? x + (t * n_step + j) * n : y + (t * n_step + n_step - 1) * n;
+  for (int k = 0; k < n; ++k) out[r * n + k] = src[k];
+}
+}  // namespace kmpc
+
 using namespace kmpc;
 
 
@@ -349,6 +366,44 @@ int kmpc_gram_from_snapshots(const kmpc_encoder* enc_c, int lift_mode, const dou
     rc = launch_encoder(enc, y + m0 * n, py, mc, lift_mode, as_stream(stream));
     if (rc != KMPC_OK) return rc;
     rc = kmpc_gram_accumulate(px, py, u + m0, x + m0 * n, mc, nzo, n, pack, stream);
+    if (rc != KMPC_OK) return rc;
+  }
+  return KMPC_OK;
+}
+
+// Trajectory-aware fused lift + Gram: the M = n_traj * n_step snapshots are trajectory-major and
+// CONSECUTIVE (y of snapshot j is x of snapshot j + 1 of the same trajectory, as data_generate.py
+// and kmpc_generate_snapshots produce them), so lift(y_j) == lift(x_{j+1}) bit for bit and every
+// state needs ONE encode: n_step + 1 per trajectory instead of 2 n_step.
+int kmpc_gram_from_trajectories(const kmpc_encoder* enc_c, int lift_mode, const double* x,
+                                const double* y, const double* u, int64_t n_traj, int n_step,
+                                double* pack, void* stream) {
+  if (!enc_c || !x || !y || !u || !pack || n_traj < 0 || n_step < 1) return KMPC_ERR_ARG;
+  kmpc_encoder* enc = const_cast<kmpc_encoder*>(enc_c);
+  const int nzo = kmpc_encoder_out_dim(enc, lift_mode);
+  const int n = enc->p.dims[0];
+  if (nzo > KMPC_MAX_NZ) return KMPC_ERR_UNSUPPORTED;
+  const int64_t chunk = 1 << 18;
+  if (n_step + 1 > chunk) return KMPC_ERR_UNSUPPORTED;
+  if (!enc->d_ws || enc->ws_rows < chunk) {
+    if (enc->d_ws) cudaFree(enc->d_ws);
+    enc->d_ws = nullptr;
+    if (cudaMalloc(&enc->d_ws, (size_t)2 * chunk * (KMPC_MAX_NZ + 4) * sizeof(double)) != cudaSuccess)
+      return KMPC_ERR_ALLOC;
+    enc->ws_rows = chunk;
+  }
+  double* pz = enc->d_ws;                                           // lifted rows (<= chunk x nz)
+  double* pin = enc->d_ws + (size_t)chunk * (KMPC_MAX_NZ + 4);      // gathered states (<= chunk x n)
+  const int64_t tc = chunk / (n_step + 1);                          // trajectories per chunk
+  cudaStream_t st = as_stream(stream);
+  for (int64_t t0 = 0; t0 < n_traj; t0 += tc) {
+    const int64_t nt = (n_traj - t0 < tc) ? (n_traj - t0) : tc;
+    const int64_t rows = nt * (n_step + 1), m0 = t0 * n_step;
+    traj_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(x + m0 * n, y + m0 * n, n, nt, n_step, pin);
+    KMPC_AFTER_LAUNCH();
+    int rc = launch_encoder(enc, pin, pz, rows, lift_mode, st);
+    if (rc != KMPC_OK) return rc;
+    rc = gram_accumulate_impl(pz, nullptr, u + m0, x + m0 * n, nt * n_step, nzo, n, pack, n_step, stream);
     if (rc != KMPC_OK) return rc;
   }
   return KMPC_OK;

@@ -12,6 +12,8 @@ struct LoopDev {  // passed by value to the kernels
   double* z_next;  // ctx-owned (S, nz): lift(x+)
   double* x_prev;  // ctx-owned (S, n):  x before the plant step (tank C regression)
   unsigned int* wset;  // ctx-owned (S, 2): optimal QP working set of the last step (fused kernel warm start)
+  double* qp_x;        // ctx-owned (S, N), nullable: optimal move sequence of the last step (generic kernels' warm
+                       // start); NaN in move 0 = no warm start for this scenario
 };
 
 KMPC_HD inline int loop_nzq(const kmpc_loop_config& c) { return c.nz + (c.du_aug ? 1 : 0); }
@@ -76,12 +78,25 @@ KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, const LoopShape sh, int64
   }
   KMPC_SYNCWARP();
   qp_build_warp<G>(ws, nzq, ny, N, identity, c.q, c.rw, d.b.r + s * ny, 0, nullptr);
+  // warm start: last step's optimal moves shifted by one (receding horizon; velocity form: the new
+  // last move is "hold the input").  Uniform over the warp: one cold scenario makes its warp cold.
+  bool warm = (NFAST == 0) && d.qp_x != nullptr;
+  if (warm) warm = !warp_any(!isfinite(d.qp_x[s * N]));
+  if (warm) {
+    const double* xp = d.qp_x + s * N;
+    KMPC_LANE_LOOP(i, N) ws.x[i] = (i + 1 < N) ? xp[i + 1] : (sh.du_aug ? 0.0 : xp[i]);
+    KMPC_SYNCWARP();
+  }
 #ifndef KMPC_HOSTEMU
   const int st = (NFAST > 0) ? qp_solve_fast<G, (NFAST > 0 ? NFAST : 1)>(ws, c.max_iter, c.tol)
-                             : qp_solve_warp<G>(ws, N, c.max_iter, c.tol);
+                             : qp_solve_warp<G>(ws, N, c.max_iter, c.tol, warm);
 #else
-  const int st = qp_solve_warp<G>(ws, N, c.max_iter, c.tol);
+  const int st = qp_solve_warp<G>(ws, N, c.max_iter, c.tol, warm);
 #endif
+  if (NFAST == 0 && d.qp_x != nullptr && valid) {
+    const bool ok = !(st & (KMPC_STATUS_NONFINITE | KMPC_STATUS_MAXITER));   // else: cold start next step
+    KMPC_LANE_LOOP(i, N) d.qp_x[s * N + i] = ok ? ws.x[i] : NAN;
+  }
   if (KMPC_LANE0 && valid) {
     const double move = ws.x[0];
     const double u = sh.du_aug ? uprev + move : move;

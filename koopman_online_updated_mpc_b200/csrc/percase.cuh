@@ -479,42 +479,57 @@ KMPC_DEV void qp_gradient(const QpWs& ws, int N) {
 // phases (its x and W are frozen) until every group of the warp is done.
 constexpr int kPdasIters = 8;
 
+// `warm` (uniform over the warp): ws.x already holds a start point -- the previous step's optimal move
+// sequence shifted by one move (receding horizon).  It is clipped into the box, every variable at
+// a bound enters the working set, and the monotone primal method runs from there: when the optimal
+// set moves by a few bounds per step this costs a few factorisations, where a cold start needs
+// one per sweep and then one per bound of the final set whenever the sweeps cycle (Tank: 10 - 25).
 template <int G>
-KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol) {
+KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol, bool warm = false) {
   int status = 0;
-  KMPC_LANE_LOOP(i, N) {
-    ws.W[i] = 0;
-    ws.p[i] = -ws.f[i];
-  }
-  KMPC_SYNCWARP();
-  status |= qp_chol_masked<G>(ws, N);
-  qp_chol_solve<G>(ws, N);
   int any = 0;
   double fmaxabs = 0.0;
-  KMPC_LANE_LOOP(i, N) {
-    double xi = ws.p[i];
-    int w = 0;
-    if (xi < ws.lb[i]) {
-      w = -1;
-      xi = ws.lb[i];
-    } else if (xi > ws.ub[i]) {
-      w = 1;
-      xi = ws.ub[i];
+  if (!warm) {
+    KMPC_LANE_LOOP(i, N) {
+      ws.W[i] = 0;
+      ws.p[i] = -ws.f[i];
     }
-    ws.W[i] = w;
-    ws.x[i] = xi;
-    any |= (w != 0);
-    fmaxabs = fmax(fmaxabs, fabs(ws.f[i]));
+    KMPC_SYNCWARP();
+    status |= qp_chol_masked<G>(ws, N);
+    qp_chol_solve<G>(ws, N);
+    KMPC_LANE_LOOP(i, N) {
+      double xi = ws.p[i];
+      int w = 0;
+      if (xi < ws.lb[i]) {
+        w = -1;
+        xi = ws.lb[i];
+      } else if (xi > ws.ub[i]) {
+        w = 1;
+        xi = ws.ub[i];
+      }
+      ws.W[i] = w;
+      ws.x[i] = xi;
+      any |= (w != 0);
+      fmaxabs = fmax(fmaxabs, fabs(ws.f[i]));
+    }
+    any = group_or<G>(any);
+  } else {
+    KMPC_LANE_LOOP(i, N) {
+      const double xi = fmin(fmax(ws.x[i], ws.lb[i]), ws.ub[i]);
+      ws.x[i] = xi;
+      ws.W[i] = xi <= ws.lb[i] ? -1 : (xi >= ws.ub[i] ? 1 : 0);
+      fmaxabs = fmax(fmaxabs, fabs(ws.f[i]));
+    }
+    any = 1;
   }
-  any = group_or<G>(any);
   fmaxabs = group_max<G>(fmaxabs);
   KMPC_SYNCWARP();
   const double mtol = tol * fmax(1.0, fmaxabs);
   bool done = !any;
-  if (warp_any(!done)) qp_gradient<G>(ws, N);  // grad at the clipped start; refreshed after each step
+  if (warp_any(!done)) qp_gradient<G>(ws, N);  // grad at the start point; refreshed after each step
   for (int it = 0; it < max_iter; ++it) {
     if (!warp_any(!done)) break;
-    const bool pdas = it < kPdasIters;  // uniform over the warp
+    const bool pdas = !warm && it < kPdasIters;  // uniform over the warp
     KMPC_LANE_LOOP(i, N) ws.p[i] = (ws.W[i] == 0) ? -ws.grad[i] : 0.0;
     KMPC_SYNCWARP();
     const int cst = qp_chol_masked<G>(ws, N);

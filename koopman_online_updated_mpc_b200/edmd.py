@@ -40,6 +40,29 @@ def gram_from_snapshots(encoder, x, y, u, pack=None, mode=None):
     return pack
 
 
+def gram_from_trajectories(encoder, x, y, u, n_step, pack=None, mode=None, verify=False):
+    """Fused lift + Gram over CONSECUTIVE trajectory-major snapshots (what data_generate.py:63-74
+    returns: y of snapshot j is x of snapshot j + 1 of the same trajectory): every state is lifted
+    once, n_step + 1 encodes per trajectory instead of 2 n_step.  `verify=True` checks the
+    precondition on the device (synchronises)."""
+    x_d, y_d = to_dev(x), to_dev(y)
+    u_d = to_dev(u).reshape(-1)
+    M, n = x_d.shape
+    if M % n_step:
+        raise ValueError("%d snapshots are not a whole number of %d-step trajectories" % (M, n_step))
+    if verify:
+        xv, yv = x_d.view(-1, n_step, n), y_d.view(-1, n_step, n)
+        if not torch.equal(yv[:, :-1], xv[:, 1:]):
+            raise ValueError("snapshots are not consecutive within trajectories: use gram_from_snapshots")
+    mode = encoder.mode if mode is None else mode
+    nz = encoder.out_dim(mode)
+    if pack is None:
+        pack = torch.zeros(gram_pack_len(nz, n), dtype=torch.float64, device=x_d.device)
+    _lib.check(_lib.lib().kmpc_gram_from_trajectories(encoder.handle, mode, ptr(x_d), ptr(y_d), ptr(u_d),
+                                                      M // n_step, int(n_step), ptr(pack), stream_ptr()))
+    return pack
+
+
 def edmd_solve(pack, nz, n=2, c_variant=C_PYTHON):
     """pack -> A (nz,nz), B (nz,1), C (n,nz), status (int tensor, KMPC_STATUS_PIVOT on failure)."""
     dev = pack.device

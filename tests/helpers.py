@@ -189,6 +189,7 @@ class EmuClosedLoop:
             params_pre=dp(self.params_pre), params_post=dp(self.params_post), cx=dp(self.cx),
             log_x=dp(self.log_x), log_u=dp(self.log_u), status=dp(self.status), log_capacity=log_steps)
         self.step = 0
+        self.qp_x = np.full((S, spec.N), np.nan)   # QP warm start carried from step to step (kmpc_ctx does the same)
 
     def run(self, T):
         nl = len(self.Ws) if self.Ws else 0
@@ -202,7 +203,7 @@ class EmuClosedLoop:
         else:
             Wp = bp = dm = None
         hostemu().emu_closed_loop(ctypes.byref(self.cfg), ctypes.byref(self.buf), int(T), self.rls_started,
-                                  ctypes.c_int64(self.step), nl, dm, Wp, bp)
+                                  ctypes.c_int64(self.step), nl, dm, Wp, bp, dp(self.qp_x))
         self.step += T
         if self.spec.update:
             self.rls_started = 1

@@ -143,7 +143,7 @@ static void host_lift(const kmpc_loop_config& c, const kmpc_loop_buffers& b, int
 
 int emu_closed_loop(const kmpc_loop_config* cfg, const kmpc_loop_buffers* buf, int T,
                     int rls_started, int64_t start_step, int n_layers, const int* dims,
-                    const double* const* W, const double* const* bias) {
+                    const double* const* W, const double* const* bias, double* qp_x) {
   LoopDev d;
   d.c = *cfg;
   d.b = *buf;
@@ -153,6 +153,8 @@ int emu_closed_loop(const kmpc_loop_config* cfg, const kmpc_loop_buffers* buf, i
   std::vector<double> znext((size_t)c.S * c.nz), xprev((size_t)c.S * c.n);
   d.z_next = znext.data();
   d.x_prev = xprev.data();
+  d.wset = nullptr;
+  d.qp_x = qp_x;   // (S, N) caller-owned warm-start move sequences (NaN = none), nullable (always cold)
   const bool identity = c.out_mode == KMPC_OUT_IDENTITY;
   std::vector<double> qws(qp_ws_doubles(loop_nzq(c), loop_ny(c), c.N, identity) + 8);
   std::vector<double> rws(rls_ws_doubles(c.nz, c.n) + 8);

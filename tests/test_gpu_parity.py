@@ -550,3 +550,21 @@ def test_open_loop_predictor_matches_reference_run(name, wsys, row):
         np.testing.assert_allclose(tYs[s], oY, rtol=0, atol=1e-11)
         np.testing.assert_allclose(dXs[s], oD, rtol=0, atol=1e-11)
         assert abs(rm[s] - opredict.rmse(oY, Xs, T2, row)) < 1e-13
+
+
+def test_gram_from_trajectories_equals_gram_from_snapshots():
+    """One encode per state on consecutive trajectory-major snapshots == two encodes per snapshot."""
+    from koopman_online_updated_mpc_b200 import data_generate as DG, edmd as E
+    rs = np.random.RandomState(7)
+    for wsys, n_traj, n_step in (("duffing", 37, 11), ("tank", 64, 20), ("duffing", 3000, 100)):
+        enc = K.Encoder.from_file(H.weights_path(wsys))
+        x0 = rs.uniform(0.1, 1.5, (n_traj, 2))
+        u0 = rs.uniform(-1, 1, (n_step, n_traj))
+        X, Y, U = DG.generate_snapshots(x0, u0, oplant.DUFFING_PRE)
+        a = E.gram_from_snapshots(enc, X, Y, U).cpu().numpy()
+        b = E.gram_from_trajectories(enc, X, Y, U, n_step, verify=True).cpu().numpy()
+        assert a[-1] == b[-1] == n_traj * n_step
+        np.testing.assert_allclose(b, a, rtol=1e-12, atol=1e-12 * np.abs(a).max())
+    with pytest.raises(ValueError):     # shuffled snapshots are not consecutive: refused when verified
+        perm = torch.randperm(X.shape[0], device=X.device)
+        E.gram_from_trajectories(enc, X[perm], Y[perm], U[perm], n_step, verify=True)
