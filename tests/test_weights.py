@@ -61,3 +61,35 @@ def test_reference_pkl_equals_reference_mat():
     Wg, _ = weights.load_encoder_weights(H.weights_path("duffing"))
     Wp, _ = weights.load_encoder_weights(os.path.join(H.REF, "AutoEncoder_20220418_duffing_2.pkl"))
     assert all(np.array_equal(a, b) for a, b in zip(Wg, Wp))
+
+
+def test_mat_writers_use_the_reference_layouts(tmp_path):
+    """io_mat writes model_weights.mat / NN_Encoder.mat / *_trajectory.mat in the layouts of
+    duffing.py:61-64, 1172 and 344 (the reference's own NN_Encoder.mat head is the layout fixture)."""
+    import scipy.io as sio
+    from koopman_online_updated_mpc_b200 import io_mat, weights as W
+    Ws, bs = H.oracle_weights("duffing")
+    p = tmp_path / "model_weights.mat"
+    io_mat.save_model_weights(p, Ws, bs)
+    m = sio.loadmat(p)
+    ref = sio.loadmat(H.weights_path("duffing"))          # written with the reference's own recipe
+    for k in ("W1", "W2", "W3", "W4", "b1", "b2", "b3", "b4"):
+        assert m[k].shape == ref[k].shape and np.array_equal(m[k], ref[k])
+    Ws2, bs2 = W.load_mat(p)
+    assert all(np.array_equal(a, b) for a, b in zip(Ws, Ws2)) and all(np.array_equal(a, b) for a, b in zip(bs, bs2))
+    g = H.golden("vdp_nn_encoder_head.npz")
+    q = tmp_path / "NN_Encoder.mat"
+    io_mat.save_nn_encoder(q, g["X_Collection_NO"], g["X_Collection"], g["U_Collection"])
+    m = sio.loadmat(q)
+    for k in ("X_Collection_NO", "X_Collection", "U_Collection"):
+        assert m[k].shape == g[k].shape and np.array_equal(m[k], g[k])
+    with pytest.raises(ValueError):
+        io_mat.save_nn_encoder(q, g["X_Collection_NO"][:, :5], g["X_Collection"], g["U_Collection"])
+    gp = H.golden("ref_duffing_predict.npz")
+    t = tmp_path / "DuffingPlot_trajectory.mat"
+    io_mat.save_trajectory(t, gp["X_head"], gp["Y_head"], gp["U_head"], gp["test_Y"], gp["decoder_X"], test_X=gp["test_X"])
+    m = sio.loadmat(t)
+    T = int(gp["plotTime"])
+    assert m["test_Y"].shape == (2, T) and m["decoder_X"].shape == (8, T) and m["marker_X"].shape == (8, T // 10)
+    np.testing.assert_allclose(m["marker_X"], gp["marker_X"], rtol=0, atol=1e-12)
+    assert m["marker_T"].shape[1] == T // 10 and m["Uplot"].shape[1] == T
