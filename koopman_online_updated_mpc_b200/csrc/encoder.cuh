@@ -233,13 +233,13 @@ __device__ __forceinline__ void lift_kloop(const double* __restrict__ ap, const 
 // One unit through all layers.  in0: layer-0 input, k-major in0[k * 8 + row] (rows [n, inpad[0]) zero);
 // bufA / bufB: ping-pong activation buffers (p.actw * kActPitch >= 64 W doubles each; the split-K
 // partial sums of the last layer go to the one that layer does not read; in0 and y may live inside
-// bufB); y: 64 doubles, y[row * 8 + col] (before the subtraction of theta(0)).
+// bufB, outside the first 64 W doubles); y[row * ypitch + col] (before the subtraction of theta(0)).
 // The caller synchronises the group before the call (in0 visible, buffers free); ends with a group
 // barrier (y visible to the group, buffers free).
 template <int W>
 __device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0, double* bufA, double* bufB,
-                                          double* y, const double* wsm, uint64_t* bars, int lw, int lane,
-                                          int bar_id) {
+                                          double* y, int ypitch, const double* wsm, uint64_t* bars, int lw,
+                                          int lane, int bar_id) {
   constexpr int MT = (KMPC_MAX_WIDTH / 8 + W - 1) / W;   // n-tiles per warp at the widest layer
   const int gid = lane >> 2, tig = lane & 3;   // mma fragment coordinates
   const double* src = in0;
@@ -287,36 +287,67 @@ __device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0,
     src = dst;
     dst = (dst == bufA) ? bufB : bufA;
   }
-  // last layer: one n-tile (out <= 8), K split over the warps, two accumulator chains per warp
+  // last layer.  One n-tile (out <= 8): K split over the warps, two accumulator chains per warp,
+  // partial sums through `dst`.  More n-tiles (Tank: out = 10): tiles over the warps like a hidden
+  // layer, no ReLU.  Output y[row * ypitch + col].
   {
     const int l = nl - 1;
     const int ksteps = p.inpad[l] >> 2, out = p.dims[l + 1], ws = p.wstride[l];
+    const int nt = (out + 7) >> 3;
     mbar_wait(&bars[l], 0);
     const double* wt = wsm + p.woff[l];
     const double* bias = wt + p.inpad[l] * ws;
-    const int per = (ksteps + W - 1) / W;
-    const int kb = min(lw * per, ksteps), ke = min(kb + per, ksteps);
     const double* ap = src + tig * kActPitch + gid;
-    const double* bp = wt + tig * ws + gid;
-    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    if (nt == 1) {
+      const int per = (ksteps + W - 1) / W;
+      const int kb = min(lw * per, ksteps), ke = min(kb + per, ksteps);
+      const double* bp = wt + tig * ws + gid;
+      double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
 #pragma unroll 1
-    for (int ks = kb; ks + 1 < ke; ks += 2) {
-      const double a0 = ap[ks * (4 * kActPitch)], b0 = bp[ks * 4 * ws];
-      const double a1 = ap[(ks + 1) * (4 * kActPitch)], b1 = bp[(ks + 1) * 4 * ws];
-      dmma_m8n8k4(c0, c1, a0, b0);
-      dmma_m8n8k4(d0, d1, a1, b1);
-    }
-    if ((ke - kb) & 1) dmma_m8n8k4(c0, c1, ap[(ke - 1) * (4 * kActPitch)], bp[(ke - 1) * 4 * ws]);
-    double* part = dst;
-    *reinterpret_cast<double2*>(part + lw * 64 + gid * 8 + 2 * tig) = make_double2(c0 + d0, c1 + d1);
-    group_barrier<W * 32>(bar_id);
-    const int t = lw * 32 + lane;
-    if (t < 64) {
-      const int col = t & 7;
-      double s = part[t];
+      for (int ks = kb; ks + 1 < ke; ks += 2) {
+        const double a0 = ap[ks * (4 * kActPitch)], b0 = bp[ks * 4 * ws];
+        const double a1 = ap[(ks + 1) * (4 * kActPitch)], b1 = bp[(ks + 1) * 4 * ws];
+        dmma_m8n8k4(c0, c1, a0, b0);
+        dmma_m8n8k4(d0, d1, a1, b1);
+      }
+      if ((ke - kb) & 1) dmma_m8n8k4(c0, c1, ap[(ke - 1) * (4 * kActPitch)], bp[(ke - 1) * 4 * ws]);
+      double* part = dst;
+      *reinterpret_cast<double2*>(part + lw * 64 + gid * 8 + 2 * tig) = make_double2(c0 + d0, c1 + d1);
+      group_barrier<W * 32>(bar_id);
+      const int t = lw * 32 + lane;
+      if (t < 64) {
+        const int row = t >> 3, col = t & 7;
+        double s = part[t];
 #pragma unroll
-      for (int w = 1; w < W; ++w) s += part[w * 64 + t];
-      y[t] = (col < out) ? s + bias[col] : 0.0;
+        for (int w = 1; w < W; ++w) s += part[w * 64 + t];
+        if (col < out) y[row * ypitch + col] = s + bias[col];
+      }
+    } else {
+      double c[MT][2];
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        const int tile = lw + W * j;
+        const double2 bb = (tile < nt) ? *reinterpret_cast<const double2*>(bias + tile * 8 + 2 * tig)
+                                       : make_double2(0.0, 0.0);
+        c[j][0] = bb.x;
+        c[j][1] = bb.y;
+      }
+      const double* bp = wt + tig * ws + lw * 8 + gid;
+      const int my_nt = (nt > lw) ? ((nt - lw + W - 1) / W) : 0;
+      switch (my_nt) {   // a last layer wider than 2 W tiles is not a lift (fused_eligible / units_eligible)
+        case 2: lift_kloop<2, W, MT>(ap, bp, ksteps, ws, c); break;
+        case 1: lift_kloop<1, W, MT>(ap, bp, ksteps, ws, c); break;
+        default: break;
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int tile = lw + W * j;
+        if (tile < nt) {
+          const int col = tile * 8 + 2 * tig;
+          if (col < out) y[gid * ypitch + col] = c[j][0];
+          if (col + 1 < out) y[gid * ypitch + col + 1] = c[j][1];
+        }
+      }
     }
     group_barrier<W * 32>(bar_id);
   }

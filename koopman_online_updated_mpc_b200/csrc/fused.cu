@@ -408,7 +408,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
   const int sc = tid >> 3, l = tid & 7;
   // quarter = 2 warps = 8 scenarios = one lift unit: its own region (ping-pong activations aliasing
   // its scenarios' scratch, layer-0 block, lift outputs) and named barrier; quarters never wait for
-  // each other inside the step loop
+  // each other inside the step loop.  Quarters q and q + 2 share two schedulers: the warp that owns
+  // the odd 13th n-tile of a 100-wide layer alternates between them (13 tile columns per scheduler)
   const int quarter = tid >> 6, wl = (tid >> 5) & 1, qbar = 1 + quarter;
   double* region = smem + quarter * a.sm.region;
   double* scr = region + (sc & 7) * kScr;
@@ -683,7 +684,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
         quarter_barrier(qbar);
         if (TIMED) tq += clock64() - c0, c0 = clock64();
         if (!(a.dbg_skip & 2))
-          lift_unit<2>(a.p, in0, region, region + a.sm.actbuf, yout, wsm, bars, wl, tid & 31, qbar);
+          lift_unit<2>(a.p, in0, region, region + a.sm.actbuf, yout, FNZ, wsm, bars, wl ^ ((quarter >> 1) & 1), tid & 31, qbar);
         yl = yout[(sc & 7) * FNZ + l];
         if (c.lift_mode != KMPC_LIFT_RAW) yl -= a.p.z0[l];
         if (TIMED) tl += clock64() - c0, c0 = clock64();
