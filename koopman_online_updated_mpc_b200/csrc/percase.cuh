@@ -389,10 +389,149 @@ KMPC_DEV void qp_build_warp(const QpWs& ws, int nzq, int ny, int N, bool identit
   }
 }
 
+#ifndef KMPC_HOSTEMU
+// ---- GPU versions of the factorisation, the triangular solves and the gradient -----------------
+// Lane l of the group OWNS rows l, l + G, ... of the packed lower triangle (slots; N <= 64 gives
+// at most 64 / G of them).  A row's entries are only ever written by its owner, so
+//   * the left-looking column step needs ONE warp synchronisation per column (row j, read by
+//     everybody in later columns), the pivot travels by shuffle, the dot products run on four
+//     independent accumulators over row pointers hoisted out of the loop (the triangular numbers
+//     T(i) mod 16 are a permutation of 0..15 over any 16 consecutive i, so lanes reading
+//     L[T(i) + k] hit distinct banks);
+//   * the triangular solves keep the right-hand side in registers and broadcast y_j / x_j with a
+//     shuffle: no synchronisation at all.
+// The host emulator (tests/hostemu) runs the lane-loop versions below; results agree to rounding.
+constexpr int kQpSlotsMax = KMPC_MAX_HORIZON / 16;
+
+template <int G>
+__device__ __forceinline__ int qp_chol_masked_rows(const QpWs& ws, int N) {
+  constexpr int SLOTS = KMPC_MAX_HORIZON / G;
+  const int lane = threadIdx.x & (G - 1);
+  int status = 0;
+  bool mrow[SLOTS];
+#pragma unroll
+  for (int sl = 0; sl < SLOTS; ++sl) {
+    const int i = lane + sl * G;
+    mrow[sl] = (i < N) ? (ws.W[i] != 0) : true;
+  }
+  for (int j = 0; j < N; ++j) {
+    const bool mj = ws.W[j] != 0;
+    const double* rowj = ws.L + tri(j, 0);
+    double sv[SLOTS], dmine = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+      const int i = lane + sl * G;
+      double v = 0.0;
+      if (i >= j && i < N && !mj && !mrow[sl]) {
+        const double* rowi = ws.L + tri(i, 0);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int k = 0;
+        for (; k + 3 < j; k += 4) {
+          s0 = fma(rowi[k], rowj[k], s0);
+          s1 = fma(rowi[k + 1], rowj[k + 1], s1);
+          s2 = fma(rowi[k + 2], rowj[k + 2], s2);
+          s3 = fma(rowi[k + 3], rowj[k + 3], s3);
+        }
+        for (; k < j; ++k) s0 = fma(rowi[k], rowj[k], s0);
+        v = 2.0 * ws.H[tri(i, j)] - ((s0 + s1) + (s2 + s3));
+      }
+      sv[sl] = v;
+      if (i == j) dmine = v;
+    }
+    double d = __shfl_sync(0xffffffffu, dmine, j & (G - 1), G);
+    if (mj) d = 1.0;
+    const double floor_j = mj ? 0.0 : kPivotFloor * (2.0 * ws.H[tri(j, j)]);
+    if (!(d > floor_j)) {  // numerically semi-definite: regularise and flag (oracle/mpc.py PIVOT_FLOOR)
+      status |= KMPC_STATUS_PIVOT;
+      d = floor_j;
+    }
+    const double inv = rsqrt(d);
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+      const int i = lane + sl * G;
+      if (i == j) {
+        ws.L[tri(j, j)] = d * inv;
+        ws.invd[j] = inv;
+      } else if (i > j && i < N) {
+        ws.L[tri(i, j)] = sv[sl] * inv;
+      }
+    }
+    __syncwarp();
+  }
+  return status;
+}
+
+template <int G>
+__device__ __forceinline__ void qp_chol_solve_rows(const QpWs& ws, int N) {
+  constexpr int SLOTS = KMPC_MAX_HORIZON / G;
+  const int lane = threadIdx.x & (G - 1);
+  double pr[SLOTS];
+#pragma unroll
+  for (int sl = 0; sl < SLOTS; ++sl) pr[sl] = (lane + sl * G < N) ? ws.p[lane + sl * G] : 0.0;
+  // forward: y_j = p_j / L_jj, then p_i -= L_ij y_j for the rows below
+#pragma unroll
+  for (int so = 0; so < SLOTS; ++so) {
+    for (int j = so * G; j < N && j < (so + 1) * G; ++j) {
+      const double yj = __shfl_sync(0xffffffffu, pr[so], j & (G - 1), G) * ws.invd[j];
+#pragma unroll
+      for (int sl = 0; sl < SLOTS; ++sl) {
+        const int i = lane + sl * G;
+        if (i > j && i < N) pr[sl] = fma(-ws.L[tri(i, j)], yj, pr[sl]);
+      }
+      if (lane == (j & (G - 1))) pr[so] = yj;
+    }
+  }
+  // backward: x_j = y_j / L_jj, then y_i -= L_ji x_j for the rows above (row j of L: coalesced)
+#pragma unroll
+  for (int so = SLOTS - 1; so >= 0; --so) {
+    const int jhi = (N < (so + 1) * G ? N : (so + 1) * G) - 1;
+    for (int j = jhi; j >= so * G; --j) {
+      const double xj = __shfl_sync(0xffffffffu, pr[so], j & (G - 1), G) * ws.invd[j];
+      const double* rowj = ws.L + tri(j, 0);
+#pragma unroll
+      for (int sl = 0; sl < SLOTS; ++sl) {
+        const int i = lane + sl * G;
+        if (i < j) pr[sl] = fma(-rowj[i], xj, pr[sl]);
+      }
+      if (lane == (j & (G - 1))) pr[so] = xj;
+    }
+  }
+#pragma unroll
+  for (int sl = 0; sl < SLOTS; ++sl)
+    if (lane + sl * G < N) ws.p[lane + sl * G] = pr[sl];
+  __syncwarp();
+}
+
+template <int G>
+__device__ __forceinline__ void qp_gradient_rows(const QpWs& ws, int N) {
+  const int lane = threadIdx.x & (G - 1);
+  for (int i = lane; i < N; i += G) {
+    const double* rowi = ws.H + tri(i, 0);
+    double s0 = 0.0, s1 = 0.0;
+    int j = 0;
+    for (; j + 1 <= i; j += 2) {
+      s0 = fma(rowi[j], ws.x[j], s0);
+      s1 = fma(rowi[j + 1], ws.x[j + 1], s1);
+    }
+    if (j <= i) s0 = fma(rowi[j], ws.x[j], s0);
+    const double* col = ws.H + tri(i + 1, 0) + i;   // H[j][i], j = i + 1 ..: stride j + 1
+    for (j = i + 1; j < N; ++j) {
+      s1 = fma(col[0], ws.x[j], s1);
+      col += j + 1;
+    }
+    ws.grad[i] = 2.0 * (s0 + s1) + ws.f[i];
+  }
+  __syncwarp();
+}
+#endif  // !KMPC_HOSTEMU
+
 // Cholesky of the free block of 2H into ws.L (masked rows/cols become identity rows).
 // Returns KMPC_STATUS_PIVOT if a pivot was not positive.
 template <int G>
 KMPC_DEV int qp_chol_masked(const QpWs& ws, int N) {
+#ifndef KMPC_HOSTEMU
+  return qp_chol_masked_rows<G>(ws, N);
+#else
   int status = 0;
   for (int j = 0; j < N; ++j) {
     const bool mj = ws.W[j] != 0;  // warp-uniform
@@ -427,11 +566,15 @@ KMPC_DEV int qp_chol_masked(const QpWs& ws, int N) {
     KMPC_SYNCWARP();
   }
   return status;
+#endif
 }
 
 // Solve (L L') p = rhs in place in ws.p (rhs must be zero on masked entries).
 template <int G>
 KMPC_DEV void qp_chol_solve(const QpWs& ws, int N) {
+#ifndef KMPC_HOSTEMU
+  qp_chol_solve_rows<G>(ws, N);
+#else
   for (int j = 0; j < N; ++j) {  // forward, column oriented
     const double yj = ws.p[j] * ws.invd[j];
     KMPC_SYNCWARP();
@@ -455,17 +598,22 @@ KMPC_DEV void qp_chol_solve(const QpWs& ws, int N) {
     }
     KMPC_SYNCWARP();
   }
+#endif
 }
 
 // grad = 2 H x + f
 template <int G>
 KMPC_DEV void qp_gradient(const QpWs& ws, int N) {
+#ifndef KMPC_HOSTEMU
+  qp_gradient_rows<G>(ws, N);
+#else
   KMPC_LANE_LOOP(i, N) {
     double s = 0.0;
     for (int j = 0; j < N; ++j) s += ws.H[i >= j ? tri(i, j) : tri(j, i)] * ws.x[j];
     ws.grad[i] = 2.0 * s + ws.f[i];
   }
   KMPC_SYNCWARP();
+#endif
 }
 
 // Exact solve of  min x'Hx + f'x,  lb <= x <= ub  (oracle/mpc.py solve_box_qp_exact is the same
