@@ -96,6 +96,11 @@ __device__ __forceinline__ void encoder_weights_issue(const EncParams& p, double
   }
 }
 
+// every thread that is going to read the weights: wait until all layers have landed (once per kernel)
+__device__ __forceinline__ void encoder_weights_wait_all(const EncParams& p, uint64_t* bars) {
+  for (int l = 0; l < p.n_layers; ++l) mbar_wait(&bars[l], 0);
+}
+
 // k-loop of one layer for a warp that owns NT n-tiles (two m-tiles each): 2 NT DMMAs per k-step
 template <int NT>
 __device__ __forceinline__ void encoder_kloop(const double* __restrict__ ap, const double* __restrict__ bp,
@@ -234,12 +239,12 @@ __device__ __forceinline__ void lift_kloop(const double* __restrict__ ap, const 
 // bufA / bufB: ping-pong activation buffers (p.actw * kActPitch >= 64 W doubles each; the split-K
 // partial sums of the last layer go to the one that layer does not read; in0 and y may live inside
 // bufB, outside the first 64 W doubles); y[row * ypitch + col] (before the subtraction of theta(0)).
-// The caller synchronises the group before the call (in0 visible, buffers free); ends with a group
-// barrier (y visible to the group, buffers free).
+// The caller has waited for the weights (encoder_weights_wait_all) and synchronises the group before
+// the call (in0 visible, buffers free); ends with a group barrier (y visible, buffers free).
 template <int W>
 __device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0, double* bufA, double* bufB,
-                                          double* y, int ypitch, const double* wsm, uint64_t* bars, int lw,
-                                          int lane, int bar_id) {
+                                          double* y, int ypitch, const double* wsm, int lw, int lane,
+                                          int bar_id) {
   constexpr int MT = (KMPC_MAX_WIDTH / 8 + W - 1) / W;   // n-tiles per warp at the widest layer
   const int gid = lane >> 2, tig = lane & 3;   // mma fragment coordinates
   const double* src = in0;
@@ -248,7 +253,6 @@ __device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0,
   for (int l = 0; l + 1 < nl; ++l) {
     const int ksteps = p.inpad[l] >> 2, out = p.dims[l + 1], ws = p.wstride[l];
     const int nt = (out + 7) >> 3;
-    mbar_wait(&bars[l], 0);   // layer l's weights have landed (returns at once after the first unit)
     const double* wt = wsm + p.woff[l];
     const double* bias = wt + p.inpad[l] * ws;
     double c[MT][2];
@@ -294,7 +298,6 @@ __device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0,
     const int l = nl - 1;
     const int ksteps = p.inpad[l] >> 2, out = p.dims[l + 1], ws = p.wstride[l];
     const int nt = (out + 7) >> 3;
-    mbar_wait(&bars[l], 0);
     const double* wt = wsm + p.woff[l];
     const double* bias = wt + p.inpad[l] * ws;
     const double* ap = src + tig * kActPitch + gid;

@@ -423,6 +423,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
     __syncthreads();
     if (tid == 0) encoder_weights_issue(a.p, wsm, bars);
   }
+  if (MLP) encoder_weights_wait_all(a.p, bars);   // overlaps nothing worth keeping: the first lift is a QP away
   const bool upc = (c.rls_flags & KMPC_RLS_UPDATE_C) != 0;
   const double lam = c.lambda;
   long long tq = 0, tl = 0, tr = 0, t_begin = 0;
@@ -684,7 +685,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
         quarter_barrier(qbar);
         if (TIMED) tq += clock64() - c0, c0 = clock64();
         if (!(a.dbg_skip & 2))
-          lift_unit<2>(a.p, in0, region, region + a.sm.actbuf, yout, FNZ, wsm, bars, wl ^ ((quarter >> 1) & 1), tid & 31, qbar);
+          lift_unit<2>(a.p, in0, region, region + a.sm.actbuf, yout, FNZ, wsm, wl ^ ((quarter >> 1) & 1), tid & 31, qbar);
         yl = yout[(sc & 7) * FNZ + l];
         if (c.lift_mode != KMPC_LIFT_RAW) yl -= a.p.z0[l];
         if (TIMED) tl += clock64() - c0, c0 = clock64();

@@ -184,6 +184,7 @@ encoder_units_kernel(EncParams p, UnitsSmem L, const double* __restrict__ x, dou
   if (tid == 0) encoder_weights_issue(p, wsm, bars);
   pdl_wait();   // the weight copies above do not depend on the previous kernel: only now wait for it
   pdl_launch_dependents();
+  encoder_weights_wait_all(p, bars);
   const int unit = tid >> 6, wl = (tid >> 5) & 1, t64 = tid & 63, bar = 1 + unit;
   double* region = smem + unit * L.region;
   double* io = region + L.io;
@@ -201,7 +202,7 @@ encoder_units_kernel(EncParams p, UnitsSmem L, const double* __restrict__ x, dou
       io[k * kUnitRows + r] = v;
     }
     group_barrier<64>(bar);
-    lift_unit<2>(p, io, region, region + L.actbuf, io, L.ypitch, wsm, bars, wl ^ ((unit >> 1) & 1), tid & 31, bar);   // units u, u + 2 share two schedulers: balance the odd n-tile
+    lift_unit<2>(p, io, region, region + L.actbuf, io, L.ypitch, wsm, wl ^ ((unit >> 1) & 1), tid & 31, bar);   // units u, u + 2 share two schedulers: balance the odd n-tile
     for (int e = t64; e < kUnitRows * out; e += 64) {
       const int r = e / out, c = e - r * out;
       if (row0 + r < S) {
