@@ -23,7 +23,7 @@ constexpr int kLoopThreadsMax = 256;   // large QP workspaces: one bigger block 
 
 // G lanes per scenario; NZ/N/OUT/DU > 0 give a compile-time QP shape (loops unrolled, indices
 // folded), NZ == 0 reads the shape from the config at run time.
-template <int G, int NZ, int N, int OUT, int DU, bool FAST = true>
+template <int G, int NZ, int N, int OUT, int DU>
 __global__ void __launch_bounds__(kLoopThreadsMax)
 loop_qp_plant_kernel(LoopDev d, int64_t step, int64_t log_slot) {
   extern __shared__ double smem[];
@@ -42,7 +42,7 @@ loop_qp_plant_kernel(LoopDev d, int64_t step, int64_t log_slot) {
   const int nzq = sh.nz + sh.du_aug;
   const bool identity = sh.out_mode == KMPC_OUT_IDENTITY;
   const int ny = identity ? nzq : (sh.out_mode == KMPC_OUT_C ? 2 : 1);
-  loop_qp_plant_scenario<G, (FAST && NZ > 0 && N + 1 <= G) ? N : 0>(d, sh, s, valid, step, log_slot,
+  loop_qp_plant_scenario<G>(d, sh, s, valid, step, log_slot,
                             smem + (size_t)group * qp_ws_doubles(nzq, ny, sh.N, identity));
 }
 
@@ -73,23 +73,15 @@ static bool select_launch(const kmpc_loop_config& c, LoopLaunch* L) {
   const bool identity = c.out_mode == KMPC_OUT_IDENTITY;
   const int ny = identity ? nzq : (c.out_mode == KMPC_OUT_C ? 2 : 1);
   L->qp_g = 32;
-  const bool fast = qp_fast_enabled();
-  if (!fast && c.nz == 8 && c.N == 10 && !c.du_aug && c.out_mode == KMPC_OUT_IDENTITY) {
-    L->qp = loop_qp_plant_kernel<16, 8, 10, KMPC_OUT_IDENTITY, 0, false>;
-    L->qp_g = 16;
-  } else if (!fast && c.nz == 8 && c.N == 10 && !c.du_aug && c.out_mode == KMPC_OUT_C) {
-    L->qp = loop_qp_plant_kernel<16, 8, 10, KMPC_OUT_C, 0, false>;
-    L->qp_g = 16;
-  } else if (!fast && c.nz == 10 && c.N == 20 && c.du_aug && c.out_mode == KMPC_OUT_C_ROW) {
-    L->qp = loop_qp_plant_kernel<32, 10, 20, KMPC_OUT_C_ROW, 1, false>;
-  } else if (c.nz == 8 && c.N == 10 && !c.du_aug && c.out_mode == KMPC_OUT_IDENTITY) {
+  if (c.nz == 8 && c.N == 10 && !c.du_aug && c.out_mode == KMPC_OUT_IDENTITY) {
     L->qp = loop_qp_plant_kernel<16, 8, 10, KMPC_OUT_IDENTITY, 0>;   // vanderpol.py
     L->qp_g = 16;
   } else if (c.nz == 8 && c.N == 10 && !c.du_aug && c.out_mode == KMPC_OUT_C) {
     L->qp = loop_qp_plant_kernel<16, 8, 10, KMPC_OUT_C, 0>;          // duffing.py, duffing_RBF.py
     L->qp_g = 16;
   } else if (c.nz == 10 && c.N == 20 && c.du_aug && c.out_mode == KMPC_OUT_C_ROW) {
-    L->qp = loop_qp_plant_kernel<32, 10, 20, KMPC_OUT_C_ROW, 1>;     // Tank_System.m
+    L->qp = loop_qp_plant_kernel<32, 10, 20, KMPC_OUT_C_ROW, 1>;     // Tank_System.m (16 lanes measured 2x slower:
+                                                                     // two scenarios in lock step, fewer warps)
   } else if (c.nz == 8 && c.N == 50 && !c.du_aug && c.out_mode == KMPC_OUT_C) {
     L->qp = loop_qp_plant_kernel<32, 8, 50, KMPC_OUT_C, 0>;          // BASELINE config 5
   } else {

@@ -41,16 +41,6 @@ inline cudaError_t ensure_smem(K kernel, int bytes) {
 
 constexpr int kWarpsPerBlock = 4;
 
-// debug knob: KMPC_QP_FAST=1 selects the experimental register-resident group solve (QpFast); it is
-// OFF by default because its G = 16 instantiation fails parity on the GPU (two groups per warp)
-inline bool qp_fast_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("KMPC_QP_FAST");
-    return e && e[0] == '1';
-  }();
-  return on;
-}
-
 // ---- programmatic dependent launch (PDL): the next kernel of the step is launched while the
 // current one is still running; it may do work that does not depend on its predecessor (weight
 // staging, RLS state loads) and then blocks in pdl_wait() until the predecessor has completed and

@@ -33,8 +33,7 @@ KMPC_HD inline LoopShape loop_shape(const kmpc_loop_config& c) {
 
 // QP + plant for scenario s at closed-loop step `step`; `base` = this group's smem slice;
 // `valid` = false for the padding groups of the last warp (compute, but write nothing).
-// NFAST > 0 (== the horizon, compile time, NFAST + 1 <= G) selects the register-resident QP solve.
-template <int G, int NFAST = 0>
+template <int G>
 KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, const LoopShape sh, int64_t s, bool valid,
                                      int64_t step, int64_t log_slot, double* base) {
   const kmpc_loop_config& c = d.c;
@@ -80,20 +79,15 @@ KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, const LoopShape sh, int64
   qp_build_warp<G>(ws, nzq, ny, N, identity, c.q, c.rw, d.b.r + s * ny, 0, nullptr);
   // warm start: last step's optimal moves shifted by one (receding horizon; velocity form: the new
   // last move is "hold the input").  Uniform over the warp: one cold scenario makes its warp cold.
-  bool warm = (NFAST == 0) && d.qp_x != nullptr;
+  bool warm = d.qp_x != nullptr;
   if (warm) warm = !warp_any(!isfinite(d.qp_x[s * N]));
   if (warm) {
     const double* xp = d.qp_x + s * N;
     KMPC_LANE_LOOP(i, N) ws.x[i] = (i + 1 < N) ? xp[i + 1] : (sh.du_aug ? 0.0 : xp[i]);
     KMPC_SYNCWARP();
   }
-#ifndef KMPC_HOSTEMU
-  const int st = (NFAST > 0) ? qp_solve_fast<G, (NFAST > 0 ? NFAST : 1)>(ws, c.max_iter, c.tol)
-                             : qp_solve_warp<G>(ws, N, c.max_iter, c.tol, warm);
-#else
   const int st = qp_solve_warp<G>(ws, N, c.max_iter, c.tol, warm);
-#endif
-  if (NFAST == 0 && d.qp_x != nullptr && valid) {
+  if (d.qp_x != nullptr && valid) {
     const bool ok = !(st & (KMPC_STATUS_NONFINITE | KMPC_STATUS_MAXITER));   // else: cold start next step
     KMPC_LANE_LOOP(i, N) d.qp_x[s * N + i] = ok ? ws.x[i] : NAN;
   }

@@ -777,206 +777,6 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol, bool
   return status;
 }
 
-#ifndef KMPC_HOSTEMU
-// ---------------------------------------------------------------- QP fast path ---------------
-// Same algorithm as qp_solve_warp, restructured for small compile-time N (N + 1 <= G) to cut the
-// number of shared-memory round trips: lane i < N OWNS variable i (x_i, grad_i, bounds, working-set
-// flag and row i of 2H live in its registers), lane N owns the right-hand side, the working set
-// travels as ballot masks, and the factorisation is a left-looking LDL' with the right-hand side
-// carried along as row N (forward substitution comes for free): ONE __syncwarp per column.  The
-// back substitution is done redundantly by every lane from shared memory (no synchronisation).
-//   ws.L   : unscaled rows  Lt[i][j] = L[i][j] d_j        ws.invd : 1 / d_j
-//   ws.p   : rhs in, then y = L^-1 rhs                     ws.x    : shared copy of x
-// Device only (uses ballots/shuffles directly); the generic path above is its executable
-// specification and is what tests/hostemu runs.
-template <int G, int N>
-struct QpFast {
-  static_assert(N + 1 <= G, "one lane per variable plus one for the right-hand side");
-  const QpWs& ws;
-  const int i;          // lane within the group
-  const unsigned gsh;   // bit offset of this group inside warp-wide ballots
-  double h2[N];         // row i of 2H (lanes i < N)
-  int status;
-
-  __device__ __forceinline__ QpFast(const QpWs& w)
-      : ws(w), i((int)(threadIdx.x & (G - 1))), gsh((threadIdx.x & 31) & ~(G - 1)), status(0) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) h2[j] = (i < N) ? 2.0 * ws.H[i >= j ? tri(i, j) : tri(j, i)] : 0.0;
-  }
-  __device__ __forceinline__ unsigned group_ballot(bool pred) const {
-    const unsigned m = __ballot_sync(0xffffffffu, pred);
-    return (G == 32) ? m : ((m >> gsh) & ((1u << G) - 1u));
-  }
-
-  // Solve (2H)_FF p_F = rhs_F for the free set F = ~masked (masked variables get p = 0).
-  // rhs_i is passed by the owning lane; returns p_i on lanes i < N.
-  __device__ __forceinline__ double factor_solve(unsigned masked, double rhs_i) {
-    if (i < N) ws.p[i] = ((masked >> i) & 1u) ? 0.0 : rhs_i;
-    __syncwarp();
-    const bool rowmasked = (i < N) && ((masked >> i) & 1u);
-    double ls[N];  // own row, scaled: Lt[i][k] / d_k
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const bool mj = (masked >> j) & 1u;
-      double s = 0.0;
-      if (i >= j && i <= N) {
-        if (mj) {
-          s = (i == j) ? 1.0 : 0.0;
-        } else if (!rowmasked) {
-          s = (i < N) ? h2[j] : ws.p[j];
-#pragma unroll
-          for (int k = 0; k < j; ++k) s = fma(-ls[k], ws.L[tri(j, k)], s);
-        }
-        if (i < N) ws.L[tri(i, j)] = s;   // publish the unscaled entry (row i is read when j == i)
-        else ws.p[j] = s;                 // y_j
-        if (i == j) {
-          const double floor_j = mj ? 0.0 : kPivotFloor * h2[j];
-          if (!(s > floor_j)) {
-            status |= KMPC_STATUS_PIVOT;
-            s = floor_j;
-          }
-          ws.invd[j] = __drcp_rn(s);
-        }
-      }
-      __syncwarp();
-      ls[j] = (i >= j && i <= N) ? s * ws.invd[j] : 0.0;
-    }
-    // back substitution, every lane redundantly:  x_j = invd_j (y_j - sum_{r>j} Lt[r][j] x_r)
-    double xs[N];
-    double mine = 0.0;
-#pragma unroll
-    for (int j = N - 1; j >= 0; --j) {
-      double s = ws.p[j];
-#pragma unroll
-      for (int r = j + 1; r < N; ++r) s = fma(-ws.L[tri(r, j)], xs[r], s);
-      xs[j] = s * ws.invd[j];
-      if (j == i) mine = xs[j];
-    }
-    __syncwarp();  // ws.p / ws.L are rewritten by the next factorisation
-    return mine;
-  }
-
-  // grad_i = (2H x)_i + f_i with x published through shared memory
-  __device__ __forceinline__ double gradient(double xi, double fi) {
-    if (i < N) ws.x[i] = xi;
-    __syncwarp();
-    double g = fi;
-#pragma unroll
-    for (int j = 0; j < N; ++j) g = fma(h2[j], ws.x[j], g);
-    __syncwarp();
-    return g;
-  }
-
-  __device__ __forceinline__ int solve(int max_iter, double tol) {
-    const bool var = i < N;
-    const double fi = var ? ws.f[i] : 0.0;
-    const double lbi = var ? ws.lb[i] : 0.0, ubi = var ? ws.ub[i] : 0.0;
-    double xi = factor_solve(0u, -fi);
-    int wi = 0;
-    if (var) {
-      if (xi < lbi) {
-        wi = -1;
-        xi = lbi;
-      } else if (xi > ubi) {
-        wi = 1;
-        xi = ubi;
-      }
-    }
-    const double mtol = tol * fmax(1.0, group_max<G>(fabs(fi)));
-    bool done = group_ballot(wi != 0) == 0u;
-    double gi = 0.0;
-    if (warp_any(!done)) gi = gradient(xi, fi);
-    for (int it = 0; it < max_iter; ++it) {
-      if (!warp_any(!done)) break;
-      const bool pdas = it < kPdasIters;
-      const unsigned masked = group_ballot(var && wi != 0);
-      const int st0 = status;
-      const double pi = factor_solve(masked, -gi);
-      if (done) status = st0;
-      double alpha = 1.0;
-      int block = 0x7fffffff;
-      if (!pdas) {  // ratio test (monotone fallback)
-        double a = 2.0;
-        if (var && wi == 0) {
-          if (pi > 0.0 && xi + pi > ubi) a = (ubi - xi) / pi;
-          else if (pi < 0.0 && xi + pi < lbi) a = (lbi - xi) / pi;
-        }
-        if (a < alpha) {
-          alpha = a;
-          block = i;
-        }
-        group_argmin<G>(alpha, block);
-      }
-      const bool blocked = block != 0x7fffffff;
-      double xn = xi, gn;
-      int wn = wi;
-      if (var) {
-        xn = xi + alpha * pi;
-        if (blocked && i == block) {
-          wn = pi > 0.0 ? 1 : -1;
-          xn = wn > 0 ? ubi : lbi;
-        }
-      }
-      gn = gradient(xn, fi);
-      bool finished = false;
-      if (pdas) {
-        bool rel = false, clip = false;
-        if (var) {
-          if (wn != 0) {
-            const double lam = wn < 0 ? gn : -gn;
-            if (lam < -mtol) {
-              wn = 0;
-              rel = true;
-            }
-          } else if (xn < lbi) {
-            xn = lbi;
-            wn = -1;
-            clip = true;
-          } else if (xn > ubi) {
-            xn = ubi;
-            wn = 1;
-            clip = true;
-          }
-        }
-        const bool anyclip = group_ballot(clip) != 0u;
-        const bool changed = anyclip || group_ballot(rel) != 0u;
-        finished = !changed;
-        if (warp_any(anyclip && !done)) gn = gradient(xn, fi);
-      } else {
-        double worst = INFINITY;
-        int widx = 0x7fffffff;
-        if (var && wn != 0) {
-          worst = wn < 0 ? gn : -gn;
-          widx = i;
-        }
-        group_argmin<G>(worst, widx);
-        if (!blocked) {
-          if (widx == 0x7fffffff || worst >= -mtol) finished = true;
-          else if (i == widx) wn = 0;
-        }
-      }
-      if (!done) {  // converged groups keep their state frozen
-        xi = xn;
-        gi = gn;
-        wi = wn;
-        done = finished;
-      }
-    }
-    if (!done) status |= KMPC_STATUS_MAXITER;
-    if (var) ws.x[i] = xi;
-    if (group_ballot(var && !isfinite(xi)) != 0u) status |= KMPC_STATUS_NONFINITE;
-    status = group_or<G>(status);
-    __syncwarp();
-    return status;
-  }
-};
-
-template <int G, int N>
-__device__ __forceinline__ int qp_solve_fast(const QpWs& ws, int max_iter, double tol) {
-  QpFast<G, N> q(ws);
-  return q.solve(max_iter, tol);
-}
-#endif  // !KMPC_HOSTEMU
 
 // ---------------------------------------------------------------- small SPD solve ------------
 // X = Bm * inv(G) for SPD G (n x n, row-major, destroyed) and Bm (rows x n): Cholesky of G then

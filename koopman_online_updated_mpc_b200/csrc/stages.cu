@@ -46,8 +46,8 @@ rls_update_kernel(double* __restrict__ KA, double* __restrict__ P, double* __res
 }
 
 // ------------------------------------------------------------------------------ QP -----------
-// G lanes per scenario; NFAST > 0: compile-time horizon with the register-resident solve.
-template <int G, int NFAST>
+// G lanes per scenario.
+template <int G>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 qp_first_move_kernel(const double* __restrict__ A, const double* __restrict__ B,
                      const double* __restrict__ Cy, const double* __restrict__ z0,
@@ -61,7 +61,6 @@ qp_first_move_kernel(const double* __restrict__ A, const double* __restrict__ B,
   int64_t s = (int64_t)blockIdx.x * (blockDim.x / G) + group;
   const bool valid = s < S;
   if (!valid) s = S - 1;
-  if (NFAST > 0) N = NFAST;
   const bool identity = flags & KMPC_QP_CY_IDENTITY;
   const bool shared_model = flags & KMPC_QP_SHARED_MODEL;
   const bool r_full = flags & KMPC_QP_R_FULL;
@@ -82,8 +81,7 @@ qp_first_move_kernel(const double* __restrict__ A, const double* __restrict__ B,
   const double* rs = r_full ? r + s * N * ny : r + s * ny;
   const double* pn = PN ? PN + sm * ny * ny : nullptr;
   qp_build_warp<G>(ws, nz, ny, N, identity, q, rw, rs, r_full ? ny : 0, pn);
-  const int st = (NFAST > 0) ? qp_solve_fast<G, (NFAST > 0 ? NFAST : 1)>(ws, max_iter, tol)
-                             : qp_solve_warp<G>(ws, N, max_iter, tol);
+  const int st = qp_solve_warp<G>(ws, N, max_iter, tol);
   if (!valid) return;
   if (lane == 0) {
     u0[s] = ws.x[0];
@@ -160,20 +158,15 @@ int kmpc_qp_first_move(const double* A, const double* B, const double* Cy, const
   if (!identity && !Cy) return KMPC_ERR_ARG;
   if (max_iter <= 0) max_iter = 10 * N + 20;
   if (!(tol > 0.0)) tol = 1e-10;
-  // horizons 10 (duffing.py / vanderpol.py) and 20 (Tank_System.m) have register-resident solves
+  // horizon 10 (duffing.py / vanderpol.py): 16 lanes per scenario, two scenarios per warp
   typedef void (*Kern)(const double*, const double*, const double*, const double*, const double*,
                        const double*, const double*, const double*, double, double, int, int, int,
                        int64_t, int, double*, double*, int*, int, double);
-  Kern kern = qp_first_move_kernel<32, 0>;
+  Kern kern = qp_first_move_kernel<32>;
   int g = 32;
-  if (N == 10 && !qp_fast_enabled()) {
-    kern = qp_first_move_kernel<16, 0>;
+  if (N == 10) {
+    kern = qp_first_move_kernel<16>;
     g = 16;
-  } else if (N == 10) {
-    kern = qp_first_move_kernel<16, 10>;
-    g = 16;
-  } else if (N == 20 && qp_fast_enabled()) {
-    kern = qp_first_move_kernel<32, 20>;
   }
   const int ws_bytes = qp_ws_doubles(nz, ny, N, identity) * (int)sizeof(double);
   int spb = (kWarpsPerBlock * 32) / g;
