@@ -7,20 +7,24 @@
 // scenario carries from step to step -- the model A, B, C, the lift z, the plant state and the RLS
 // state K_A, P, bar_X, bar_Q (233 doubles) -- lives in the REGISTERS of its 8 lanes, distributed by
 // rows (lane i holds row i), and touches HBM once per launch instead of once per step.  The
-// encoder weights (182 KB) are brought into shared memory once per CTA by the TMA engine and the
-// 32 x (2-100-100-100-8) MLP of a step runs on the fp64 tensor path (encoder.cuh).  Per-scenario
-// scratch (184 doubles) aliases the encoder's activation buffer: the phases of a step are
-// separated by CTA barriers.
+// encoder weights (175 KB) are brought into shared memory once per CTA by the TMA engine and the
+// 2-100-100-100-8 MLP of a step runs on the fp64 tensor path (encoder.cuh: lift_unit).
 //
-// Step schedule of a CTA (8 warps, warp w = scenarios 4w..4w+3):
+// A QUARTER (lift unit) = 2 warps = 8 scenarios = one DMMA m-tile.  It owns a region of shared memory:
+// two ping-pong activation buffers aliased by its scenarios' scratch (184 doubles each; the scratch
+// is dead while the unit lifts), the layer-0 input block and the lift outputs.  Quarters
+// synchronise only internally (named barrier, 64 threads): there is no CTA-wide barrier in the
+// step loop and the four quarters drift freely.
+//
+// Step schedule of a quarter (warp w = scenarios 4w..4w+3):
 //   QP build   lanes cooperate: Krylov chains VZ[t] = A^(t+1) z, VB[t] = A^t B (lane i = component
 //              i, vectors exchanged through shared memory), then H = q G'G + rw I and
 //              f = 2 q G'(F z - r) from lane-local partial sums reduced across the 8 lanes;
-//   QP solve   lane 0 of the scenario: exact primal-dual active-set solve (same algorithm as
-//              percase.cuh qp_solve_warp / oracle solve_box_qp_exact), compile-time horizon,
-//              Cholesky factor in shared memory, vectors in registers;
+//   QP solve   8 lanes (QpCoop): exact primal-dual active-set solve (same algorithm as percase.cuh
+//              qp_solve_warp / oracle solve_box_qp_exact), compile-time horizon, warm-started from
+//              the previous step's working set, right-looking Cholesky with replicated pivots;
 //   plant      lane 0: RK4 / tank map, logs;
-//   lift       CTA-wide: encoder_layers on the 32 new states (tensor path) or 8 RBFs per scenario;
+//   lift       quarter: lift_unit<2> on the 8 new states (tensor path) or 8 RBFs per scenario;
 //   RLS        lanes cooperate: Sherman-Morrison on P and bar_Q, K_A += y v', [A B] = K_A P,
 //              C = bar_X bar_Q (duffing.py:927-953), formula order of the reference.
 //

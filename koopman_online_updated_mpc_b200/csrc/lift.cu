@@ -9,13 +9,16 @@
 // padded ([in][out_pad], out_pad multiple of 4), packed layer after layer in one device buffer.
 // Each thread owns a 4 (scenarios) x 4 (outputs) register tile: 16 DFMA per 8 x 8-byte operands.
 //
-// encoder_mma_kernel (default): the whole packed weight set (182 KB for 2-100-100-100-8) is
+// encoder_units_kernel (default): the whole packed weight set (175 KB for 2-100-100-100-8) is
 // brought into shared memory ONCE per CTA by the TMA engine (cp.async.bulk, one mbarrier per
-// layer so layer 1 starts while layers 2.. are still in flight); CTAs are persistent over tiles;
-// the layer GEMMs run on the fp64 tensor path (mma.sync m8n8k4 f64 -- tcgen05 has no f64 kind, and
-// DMMA measures the same 37 TFLOP/s as DFMA on B200, but needs 8x fewer shared-memory wavefronts
-// per MAC, which is what bounded the CUDA-core version).  Row strides of the activation (36) and
-// weight (== 4 mod 16) arrays make every fragment load bank-conflict free.
+// layer); CTAs are persistent; the CTA is four independent lift units of 2 warps x 8 rows running
+// encoder.cuh: lift_unit<2> (ping-pong activations, one unit-local barrier per layer, software-
+// pipelined DMMA k-loop, split-K last layer).  The layer GEMMs run on the fp64 tensor path
+// (mma.sync m8n8k4 f64 -- tcgen05 has no f64 kind, and DMMA measures the same 37 TFLOP/s as DFMA on
+// B200, but needs 8x fewer shared-memory wavefronts per MAC, which is what bounded the CUDA-core
+// version).  Row strides of the weight arrays (== 4 or 12 mod 16) and the activation pitch (8) make
+// every fragment load bank-conflict free.
+// encoder_mma_kernel (nets with more than 16 outputs): same staging, CTA-wide 32-row tiles.
 // encoder_kernel (fallback for nets that do not fit 227 KB): CUDA-core 4x4 register tiles,
 // weights read from global/L2.
 #include "encoder.cuh"
