@@ -194,7 +194,14 @@ __device__ __forceinline__ void encoder_layers(const EncParams& p, const double*
 // predicated); the last layer (one n-tile) is split over the warps along K, two accumulator chains
 // per warp, and summed (+ bias) by the first 64 threads of the group.
 constexpr int kUnitRows = 8;       // scenarios per lift unit = rows of one m-tile
-constexpr int kActPitch = 8;       // doubles per activation row k (A-fragment loads are conflict free)
+constexpr int kActPitch = 8;       // doubles per activation row k
+// Activation element (k, row) lives at k * 8 + (row ^ 4 * ((k >> 1) & 1)).  64-bit shared accesses
+// are served per half-warp (16 lanes x 8 B = all 32 banks): the A fragment of an m8n8k4 DMMA reads
+// rows 0..3 (or 4..7) of four consecutive k in a half-warp, and the XOR puts the k = 2, 3 rows in the
+// other half of the 16-double window -- conflict free with no padding (measured 2-way without it).
+__host__ __device__ __forceinline__ int act_index(int k, int row) {
+  return k * kActPitch + (row ^ (((k >> 1) & 1) << 2));
+}
 
 template <int THREADS>
 __device__ __forceinline__ void group_barrier(int id) {
@@ -235,10 +242,14 @@ __device__ __forceinline__ void lift_kloop(const double* __restrict__ ap, const 
   }
 }
 
-// One unit through all layers.  in0: layer-0 input, k-major in0[k * 8 + row] (rows [n, inpad[0]) zero);
+// One unit through all layers.  in0: layer-0 input, k-major in0[act_index(k, row)] (rows [n, inpad[0]) zero);
 // bufA / bufB: ping-pong activation buffers (p.actw * kActPitch >= 64 W doubles each; the split-K
 // partial sums of the last layer go to the one that layer does not read; in0 and y may live inside
 // bufB, outside the first 64 W doubles); y[row * ypitch + col] (before the subtraction of theta(0)).
+// bufB == bufA selects IN-PLACE activations (half the shared memory, so twice the units per CTA in the
+// stand-alone encoder kernel): one more group barrier per layer between the last read and the first
+// write; in0 may then live in the pad rows of bufA (k-rows >= the widest layer) and y anywhere in
+// bufA beyond the first 64 W doubles.
 // The caller has waited for the weights (encoder_weights_wait_all) and synchronises the group before
 // the call (in0 visible, buffers free); ends with a group barrier (y visible, buffers free).
 template <int W>
@@ -249,6 +260,7 @@ __device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0,
   const int gid = lane >> 2, tig = lane & 3;   // mma fragment coordinates
   const double* src = in0;
   double* dst = bufA;
+  const bool inplace = (bufA == bufB);   // warp-uniform
   const int nl = p.n_layers;
   for (int l = 0; l + 1 < nl; ++l) {
     const int ksteps = p.inpad[l] >> 2, out = p.dims[l + 1], ws = p.wstride[l];
@@ -264,7 +276,7 @@ __device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0,
       c[j][0] = bb.x;
       c[j][1] = bb.y;
     }
-    const double* ap = src + tig * kActPitch + gid;
+    const double* ap = src + act_index(tig, gid);   // k = 4 ks + tig: the swizzle depends on tig only
     const double* bp = wt + tig * ws + lw * 8 + gid;
     const int my_nt = (nt > lw) ? ((nt - lw + W - 1) / W) : 0;   // warp-uniform
     switch (my_nt) {
@@ -278,13 +290,14 @@ __device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0,
       case 1: lift_kloop<1, W, MT>(ap, bp, ksteps, ws, c); break;
       default: break;
     }
+    if (inplace) group_barrier<W * 32>(bar_id);   // every warp is done reading what is overwritten now
 #pragma unroll
     for (int j = 0; j < MT; ++j) {
       const int tile = lw + W * j;
       if (tile < nt) {
-        const int col = tile * 8 + 2 * tig;
-        dst[col * kActPitch + gid] = relu_nan(c[j][0]);
-        dst[(col + 1) * kActPitch + gid] = relu_nan(c[j][1]);
+        const int col = tile * 8 + 2 * tig;   // col and col + 1 share (k >> 1) & 1 = tig & 1
+        dst[act_index(col, gid)] = relu_nan(c[j][0]);
+        dst[act_index(col + 1, gid)] = relu_nan(c[j][1]);
       }
     }
     group_barrier<W * 32>(bar_id);   // layer l + 1 reads what every warp has just written
@@ -300,7 +313,7 @@ __device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0,
     const int nt = (out + 7) >> 3;
     const double* wt = wsm + p.woff[l];
     const double* bias = wt + p.inpad[l] * ws;
-    const double* ap = src + tig * kActPitch + gid;
+    const double* ap = src + act_index(tig, gid);
     if (nt == 1) {
       const int per = (ksteps + W - 1) / W;
       const int kb = min(lw * per, ksteps), ke = min(kb + per, ksteps);
@@ -315,6 +328,7 @@ __device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0,
       }
       if ((ke - kb) & 1) dmma_m8n8k4(c0, c1, ap[(ke - 1) * (4 * kActPitch)], bp[(ke - 1) * 4 * ws]);
       double* part = dst;
+      if (inplace) group_barrier<W * 32>(bar_id);
       *reinterpret_cast<double2*>(part + lw * 64 + gid * 8 + 2 * tig) = make_double2(c0 + d0, c1 + d1);
       group_barrier<W * 32>(bar_id);
       const int t = lw * 32 + lane;
@@ -342,6 +356,7 @@ __device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0,
         case 1: lift_kloop<1, W, MT>(ap, bp, ksteps, ws, c); break;
         default: break;
       }
+      if (inplace) group_barrier<W * 32>(bar_id);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int tile = lw + W * j;

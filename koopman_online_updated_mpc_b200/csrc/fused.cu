@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
       if (MLP) {
         // x+ -> the unit's layer-0 block (k-major); the barrier also says that both warps of the unit
         // are done with the scratch their activations are about to overwrite
-        if (l < 4) in0[l * kUnitRows + (sc & 7)] = (l == 0) ? x1n : ((l == 1) ? x2n : 0.0);
+        if (l < 4) in0[act_index(l, sc & 7)] = (l == 0) ? x1n : ((l == 1) ? x2n : 0.0);
         quarter_barrier(qbar);
         if (TIMED) tq += clock64() - c0, c0 = clock64();
         if (!(a.dbg_skip & 2))

@@ -147,23 +147,25 @@ encoder_mma_kernel(EncParams p, const double* __restrict__ x, double* __restrict
   }
 }
 
-// Default kernel: the CTA is four independent lift units of 2 warps x 8 rows (encoder.cuh:
-// lift_unit<2>, the same code the fused closed-loop kernel runs): ping-pong activations, one
-// unit-local named barrier per layer, software-pipelined DMMA k-loop.  The units drift apart, so the
-// tensor pipe of a sub-partition keeps issuing while the other unit on it sits at a barrier.
+// Default kernel: the CTA is kEncUnits independent lift units of 2 warps x 8 rows (encoder.cuh:
+// lift_unit<2>, the same code the fused closed-loop kernel runs) with IN-PLACE activations: 6.5 KB of
+// shared memory per unit, so eight units (16 warps, four per scheduler) fit beside the weights.  The
+// units drift apart; with four warps per scheduler the tensor pipe keeps issuing while other units
+// sit at their barriers or in their epilogues (two warps per scheduler: 66 % DMMA issue rate).
+constexpr int kEncUnits = 8;
+constexpr int kEncUnitThreads = kEncUnits * 64;
 struct UnitsSmem {  // offsets in doubles
-  int region, actbuf, io, ypitch, wsm, bars, total_bytes;
+  int region, in0, yout, ypitch, wsm, bars, total_bytes;
 };
 inline UnitsSmem units_smem_layout(const EncParams& p) {
   UnitsSmem L;
   const int out = p.dims[p.n_layers];
-  L.actbuf = p.actw * kActPitch;
+  const int actbuf = p.actw * kActPitch;
   L.ypitch = (out + 1) & ~1;
-  int io = kUnitRows * L.ypitch;               // lift outputs; the layer-0 input block (4 x 8) aliases them
-  if (io < 4 * kUnitRows) io = 4 * kUnitRows;
-  L.io = 2 * L.actbuf;
-  L.region = (2 * L.actbuf + io + 1) & ~1;
-  L.wsm = 4 * L.region;
+  L.yout = 128;                                  // beyond the split-K partials (2 warps x 64)
+  L.in0 = actbuf - 4 * kUnitRows;                // the pad k-rows of the activation buffer
+  L.region = actbuf;
+  L.wsm = kEncUnits * L.region;
   L.bars = (L.wsm + p.total_w + 1) & ~1;
   L.total_bytes = (L.bars + KMPC_MAX_LAYERS) * 8;
   return L;
@@ -171,11 +173,16 @@ inline UnitsSmem units_smem_layout(const EncParams& p) {
 inline bool units_eligible(const EncParams& p, int max_smem) {
   const int out = p.dims[p.n_layers];
   if (p.n_layers < 2 || out > 16 || p.dims[0] > 4) return false;
-  if (p.actw * kActPitch < 128) return false;   // split-K partials live in a ping-pong buffer
+  int widest = 0;
+  for (int l = 1; l < p.n_layers; ++l) widest = p.dims[l] > widest ? p.dims[l] : widest;
+  // in0 lives in k-rows [actw - 4, actw): they must be pad rows of every hidden layer's OUTPUT (their
+  // weights rows are zero), and y (8 x ypitch from 128) must end below them
+  if (p.actw - 4 < widest) return false;
+  if (128 + kUnitRows * ((out + 1) & ~1) > (p.actw - 4) * kActPitch) return false;
   return units_smem_layout(p).total_bytes <= max_smem;
 }
 
-__global__ void __launch_bounds__(kMmaThreads, 1)
+__global__ void __launch_bounds__(kEncUnitThreads, 1)
 encoder_units_kernel(EncParams p, UnitsSmem L, const double* __restrict__ x, double* __restrict__ z,
                      int64_t S, int lift_mode, int out_dim, int64_t n_blocks) {
   extern __shared__ __align__(16) double smem[];
@@ -190,10 +197,11 @@ encoder_units_kernel(EncParams p, UnitsSmem L, const double* __restrict__ x, dou
   encoder_weights_wait_all(p, bars);
   const int unit = tid >> 6, wl = (tid >> 5) & 1, t64 = tid & 63, bar = 1 + unit;
   double* region = smem + unit * L.region;
-  double* io = region + L.io;
+  double* in0 = region + L.in0;
+  double* yo = region + L.yout;
   const int n = p.dims[0], out = p.dims[p.n_layers];
   const int off = (lift_mode == KMPC_LIFT_STACK) ? n : 0;
-  for (int64_t rb = (int64_t)blockIdx.x * 4 + unit; rb < n_blocks; rb += (int64_t)gridDim.x * 4) {
+  for (int64_t rb = (int64_t)blockIdx.x * kEncUnits + unit; rb < n_blocks; rb += (int64_t)gridDim.x * kEncUnits) {
     const int64_t row0 = rb * kUnitRows;
     if (t64 < 4 * kUnitRows) {   // layer-0 input, k-major, rows [n, 4) zero
       const int k = t64 >> 3, r = t64 & 7;
@@ -202,19 +210,20 @@ encoder_units_kernel(EncParams p, UnitsSmem L, const double* __restrict__ x, dou
         v = x[(row0 + r) * n + k];
         if (lift_mode == KMPC_LIFT_STACK) z[(row0 + r) * out_dim + k] = v;
       }
-      io[k * kUnitRows + r] = v;
+      in0[act_index(k, r)] = v;
     }
     group_barrier<64>(bar);
-    lift_unit<2>(p, io, region, region + L.actbuf, io, L.ypitch, wsm, wl ^ ((unit >> 1) & 1), tid & 31, bar);   // units u, u + 2 share two schedulers: balance the odd n-tile
+    // units u, u + 2, .. share two schedulers: alternate the warp that owns the odd n-tile
+    lift_unit<2>(p, in0, region, region, yo, L.ypitch, wsm, wl ^ ((unit >> 1) & 1), tid & 31, bar);
     for (int e = t64; e < kUnitRows * out; e += 64) {
       const int r = e / out, c = e - r * out;
       if (row0 + r < S) {
-        double v = io[r * L.ypitch + c];
+        double v = yo[r * L.ypitch + c];
         if (lift_mode != KMPC_LIFT_RAW) v -= p.z0[c];
         z[(row0 + r) * out_dim + off + c] = v;
       }
     }
-    group_barrier<64>(bar);   // the next block's input overwrites the outputs
+    group_barrier<64>(bar);   // the next block's layers overwrite the outputs
   }
 }
 
@@ -289,9 +298,9 @@ static int launch_encoder(const kmpc_encoder* enc, const double* x, double* z, i
   if (!units_off && units_eligible(enc->p, enc->max_smem_optin)) {
     const UnitsSmem L = units_smem_layout(enc->p);
     KMPC_CUDA(ensure_smem(encoder_units_kernel, L.total_bytes));
-    const int64_t blocks = (S + kUnitRows - 1) / kUnitRows, ctas = (blocks + 3) / 4;
+    const int64_t blocks = (S + kUnitRows - 1) / kUnitRows, ctas = (blocks + kEncUnits - 1) / kEncUnits;
     const unsigned grid = (unsigned)(ctas < enc->num_sms ? ctas : enc->num_sms);
-    KMPC_CUDA(launch_pdl(encoder_units_kernel, grid, (unsigned)kMmaThreads, (size_t)L.total_bytes, st, enc->p, L, x, z,
+    KMPC_CUDA(launch_pdl(encoder_units_kernel, grid, (unsigned)kEncUnitThreads, (size_t)L.total_bytes, st, enc->p, L, x, z,
                          S, lift_mode, out_dim, blocks));
   } else if (enc->smem_bytes > 0) {
     KMPC_CUDA(ensure_smem(encoder_mma_kernel, enc->smem_bytes));
