@@ -64,6 +64,16 @@ def test_argument_validation_without_touching_the_gpu():
     assert L.kmpc_rls_update(*([p] * 11), 0, 8, 2, 1.0, 1, None) == 0     # empty batch is a no-op
     assert L.kmpc_qp_first_move(*([p] * 8), 100.0, 1e-4, 999, 2, 8, 4, 0, p, None, None, 0, 0.0, None) == -1
     assert L.kmpc_plant_step(p, p, p, p, 0, 0, 0, 0.05, None) == 0
+    # snapshot generator / open-loop predictor / trajectory-aware Gram
+    assert L.kmpc_generate_snapshots(None, None, None, 0, 0, 0.05, 4, 10, None, None, None, None) == -1
+    assert L.kmpc_generate_snapshots(p, p, p, 7, 0, 0.05, 4, 10, p, p, p, None) == -1      # unknown plant
+    assert L.kmpc_generate_snapshots(p, p, p, 0, 0, 0.05, 0, 10, p, p, p, None) == 0       # empty set
+    assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 99, 2, 1, 10, 10, 10, 0, p, p, p, None) == -1   # nz out of range
+    assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 8, 2, 1, 10, 5, 10, 0, p, p, p, None) == -1    # stride < T
+    assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 8, 2, 1, 10, 10, 0, 0, p, p, p, None) == -1    # reset_every < 1
+    assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 8, 2, 1, 10, 10, 10, 5, p, p, p, None) == -1   # rmse row out of range
+    assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 8, 2, 0, 10, 10, 10, 0, p, p, p, None) == 0    # no sequences
+    assert L.kmpc_gram_from_trajectories(None, 0, p, p, p, 4, 10, p, None) == -1                      # no encoder
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
