@@ -309,10 +309,16 @@ int kmpc_closed_loop_steps_timed(kmpc_ctx* ctx, int T, void* stream, float* ms) 
         for (int k = 0; k < 3; ++k) share[k] += (double)h[4 * i + k] / (double)(h[4 * i + 3] > 0 ? h[4 * i + 3] : 1);
       for (int k = 0; k < 3; ++k) ms[k] = (float)(total * share[k] / (grid > 0 ? grid : 1));
       if (rc == KMPC_OK && getenv("KMPC_DEBUG_TIMING")) {
-        long long mx = 0;
-        for (int i = 0; i < grid; ++i) mx = h[4 * i + 3] > mx ? h[4 * i + 3] : mx;
-        fprintf(stderr, "[kmpc] fused timed: grid %d, T %d, %.3f ms, max CTA cycles %lld -> SM clock %.0f MHz\n",
-                grid, T, total, mx, mx / (total * 1e3));
+        long long mx = 0, mn = h[3];
+        double mean = 0.0;
+        for (int i = 0; i < grid; ++i) {
+          mx = h[4 * i + 3] > mx ? h[4 * i + 3] : mx;
+          mn = h[4 * i + 3] < mn ? h[4 * i + 3] : mn;
+          mean += (double)h[4 * i + 3] / grid;
+        }
+        // cycles of quarter 0 of every CTA: the launch lasts as long as its slowest tile
+        fprintf(stderr, "[kmpc] fused timed: grid %d, T %d, %.3f ms, CTA cycles min %lld mean %.0f max %lld -> SM clock %.0f MHz\n",
+                grid, T, total, mn, mean, mx, mx / (total * 1e3));
       }
     }
     cudaEventDestroy(e0);
