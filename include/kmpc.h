@@ -70,6 +70,19 @@ int kmpc_encoder_out_dim(const kmpc_encoder* enc, int lift_mode);
 int kmpc_encode(const kmpc_encoder* enc, const double* x, double* z, int64_t S, int lift_mode,
                 void* stream);
 
+/* Precision of the EDMD-side lift (duffing.py:152-164, the 20 000 encoder calls ahead of the regression):
+ *   KMPC_PREC_FP64  fp64 tensor path (mma.sync m8n8k4 f64), bit-compatible with the closed loop's lift;
+ *   KMPC_PREC_TC    Blackwell tensor path: tcgen05.mma kind::f16 on bf16 x 3 split operands (six piece
+ *                   products), fp32 accumulation in TMEM, weights staged by TMA tensor copies; lifted
+ *                   states agree with fp64 to ~1e-7 relative (tests/test_tc_lift.py), the Gram pack is
+ *                   still accumulated in fp64.  Nets with hidden width <= 112, out <= 16, in <= 4;
+ *                   otherwise KMPC_ERR_UNSUPPORTED (kmpc_encoder_has_tc tells in advance).           */
+#define KMPC_PREC_FP64 0
+#define KMPC_PREC_TC 1
+int kmpc_encoder_has_tc(const kmpc_encoder* enc);
+int kmpc_encode_ex(const kmpc_encoder* enc, const double* x, double* z, int64_t S, int lift_mode,
+                   int precision, void* stream);
+
 /* thin-plate RBF lift: duffing_RBF.py:20-23 (variant 0: d^2 log(d + 1e-4)); rbf.m:24-29
  * (variant 1: r2 log sqrt(r2), 0 at r = 0).  x [dev] (S, n), cx [dev] (nz, n) -> z [dev] (S, nz) */
 #define KMPC_RBF_PYTHON 0
@@ -95,6 +108,14 @@ int kmpc_gram_from_snapshots(const kmpc_encoder* enc, int lift_mode, const doubl
 int kmpc_gram_from_trajectories(const kmpc_encoder* enc, int lift_mode, const double* x,
                                 const double* y, const double* u, int64_t n_traj, int n_step,
                                 double* pack, void* stream);
+/* the same two with an explicit lift precision (KMPC_PREC_*).  One lift workspace lives in the encoder
+ * handle: concurrent calls on the SAME handle (threads or streams) are serialised by the library.   */
+int kmpc_gram_from_snapshots_ex(const kmpc_encoder* enc, int lift_mode, int precision, const double* x,
+                                const double* y, const double* u, int64_t M, double* pack,
+                                void* stream);
+int kmpc_gram_from_trajectories_ex(const kmpc_encoder* enc, int lift_mode, int precision,
+                                   const double* x, const double* y, const double* u, int64_t n_traj,
+                                   int n_step, double* pack, void* stream);
 #define KMPC_C_PYTHON 0 /* C = (X PHIX')(PHIX PHIX')^-1            duffing.py:177        */
 #define KMPC_C_JOINT 1  /* C = block of [PHIY;X] V' (V V')^-1      Tank_System.m:96-100  */
 /* A [dev] (nz,nz), B [dev] (nz,1), C [dev] (n,nz), status [dev] (1) */
@@ -149,6 +170,8 @@ int kmpc_plant_step(const double* x, const double* u, const double* params, doub
 #define KMPC_OUT_C_ROW 2    /* y = (C z)[out_row], ny=1  Tank_System.m:113      */
 #define KMPC_LIFTKIND_MLP 0
 #define KMPC_LIFTKIND_RBF 1
+#define KMPC_PATH_AUTO 0
+#define KMPC_PATH_GENERIC 1
 
 typedef struct kmpc_loop_config {
   int64_t S;
@@ -177,6 +200,10 @@ typedef struct kmpc_loop_config {
   double p0, q0;       /* RLS restart: P = p0 I, bar_Q = q0 I at the first update (step_index == 0
                           and rls_started == 0); ignored when the caller warm-starts the state */
   double tol;
+  int path;            /* KMPC_PATH_AUTO: persistent fused kernel when the shape allows it;
+                          KMPC_PATH_GENERIC: always the per-step qp_plant -> lift -> rls kernels (cross-check) */
+  int qp_cold;         /* 1: generic kernels cold-start every QP like the reference (duffing.py:634: pastRes
+                          is never written back); 0: warm start from the previous step's moves (same minimiser) */
 } kmpc_loop_config;
 
 typedef struct kmpc_loop_buffers {     /* all [dev] */
@@ -200,6 +227,10 @@ typedef struct kmpc_loop_buffers {     /* all [dev] */
   int64_t log_capacity; /* T_cap */
 } kmpc_loop_buffers;
 
+/* Streams: kmpc_ctx_create / kmpc_ctx_reset queue small memsets on the stream they are given and
+ * record an event; kmpc_closed_loop_steps* waits on that event, so create / reset / steps may use
+ * different streams.  The caller's own writes to the buffers must be ordered before the steps call
+ * by the caller.  A ctx may be used from one host thread at a time.                              */
 typedef struct kmpc_ctx kmpc_ctx;
 int kmpc_ctx_create(kmpc_ctx** out, const kmpc_loop_config* cfg, const kmpc_loop_buffers* buf,
                     const kmpc_encoder* enc /* nullable for RBF */, int rls_started,

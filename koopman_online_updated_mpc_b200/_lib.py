@@ -19,7 +19,7 @@ class LoopConfigC(_c.Structure):  # mirrors kmpc_loop_config
                 ("skip_first_barx", _i), ("shared_model", _i), ("lift_kind", _i), ("lift_mode", _i),
                 ("plant_kind", _i), ("rk4_variant", _i), ("first_post_step", _i), ("max_iter", _i),
                 ("h", _d), ("q", _d), ("rw", _d), ("lb", _d), ("ub", _d), ("u_lb", _d), ("u_ub", _d),
-                ("lam", _d), ("p0", _d), ("q0", _d), ("tol", _d)]
+                ("lam", _d), ("p0", _d), ("q0", _d), ("tol", _d), ("path", _i), ("qp_cold", _i)]
 
 
 class LoopBuffersC(_c.Structure):  # mirrors kmpc_loop_buffers
@@ -38,6 +38,10 @@ _PROTOS = {
     "kmpc_encoder_destroy": (_i, [_vp]),
     "kmpc_encoder_out_dim": (_i, [_vp, _i]),
     "kmpc_encode": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "kmpc_encode_ex": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp]),
+    "kmpc_encoder_has_tc": (_i, [_vp]),
+    "kmpc_gram_from_snapshots_ex": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "kmpc_gram_from_trajectories_ex": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "kmpc_rbf_lift": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
     "kmpc_gram_pack_len": (_i64, [_i, _i]),
     "kmpc_gram_accumulate": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp]),

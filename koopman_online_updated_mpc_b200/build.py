@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(CSRC, "_obj")
 LIB_PATH = os.path.join(PKG_DIR, "libkmpc.so")
-SOURCES = ["abi.cu", "stages.cu", "lift.cu", "edmd.cu", "predict.cu", "closed_loop.cu", "fused.cu"]
+SOURCES = ["abi.cu", "stages.cu", "lift.cu", "tc_lift.cu", "edmd.cu", "predict.cu", "closed_loop.cu", "fused.cu"]
 NVCC_FLAGS = ["-Xcompiler", "-fPIC", "-O3", "-lineinfo", "-std=c++17",
               "-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -13,6 +13,7 @@ from ._tensors import ptr, stream_ptr, to_dev
 
 OUT_C, OUT_IDENTITY, OUT_C_ROW = 0, 1, 2
 LIFTKIND_MLP, LIFTKIND_RBF = 0, 1
+PATH_AUTO, PATH_GENERIC = 0, 1
 
 
 @dataclass
@@ -44,6 +45,8 @@ class LoopSpec:
     p0: float = 1e4                # duffing.py:929-930 (pinv(1e-4 I))
     q0: float = 100.0              # duffing.py:946
     tol: float = 0.0
+    path: int = PATH_AUTO          # PATH_GENERIC: force the per-step generic kernels (cross-check of the fused one)
+    qp_cold: bool = False          # generic kernels: cold-start every QP (duffing.py:634) instead of warm starting
     params_pre: tuple = _plant.DUFFING_PRE
     params_post: tuple = _plant.DUFFING_POST
 
@@ -95,7 +98,27 @@ def make_config(spec, S, shared_model, log_steps=0):
         plant_kind=spec.plant_kind, rk4_variant=spec.rk4_variant,
         first_post_step=spec.first_post_step, max_iter=spec.max_iter, h=spec.h, q=spec.q,
         rw=spec.rw, lb=spec.lb, ub=spec.ub, u_lb=spec.u_lb, u_ub=spec.u_ub, lam=spec.lam,
-        p0=spec.p0, q0=spec.q0, tol=spec.tol)
+        p0=spec.p0, q0=spec.q0, tol=spec.tol, path=int(spec.path), qp_cold=int(spec.qp_cold))
+
+
+def _as_model(M, tail, S, name):
+    """(tail) or (1|S, tail) -> CUDA (1|S, *tail); B may come without its trailing 1."""
+    t = to_dev(M)
+    numel = tail[0] * tail[1]
+    if t.numel() == numel:
+        return t.reshape(1, *tail)
+    if t.numel() == S * numel and t.shape[0] == S:
+        return t.reshape(S, *tail)
+    raise ValueError("%s has shape %s: expected %s or (%d, %d, %d)" % (name, tuple(t.shape), tail, S, *tail))
+
+
+def _check_rls_state(st, S, nz, n):
+    want = {"KA": (S, nz, nz + 1), "P": (S, nz + 1, nz + 1), "barX": (S, n, nz), "barQ": (S, nz, nz)}
+    for k, shp in want.items():
+        t = getattr(st, k)
+        if tuple(t.shape) != shp or t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+            raise ValueError("RLSState.%s must be a contiguous CUDA float64 tensor of shape %s, got %s"
+                             % (k, shp, tuple(t.shape)))
 
 
 class ClosedLoop:
@@ -114,17 +137,19 @@ class ClosedLoop:
         self.x = to_dev(x0).reshape(-1, spec.n).clone()
         S = self.S = self.x.shape[0]
         nz, n = spec.nz, spec.n
-        A_d, B_d, C_d = to_dev(A), to_dev(B), to_dev(C)
-        shared = A_d.ndim == 2
-        if spec.update and shared:
-            A_d = A_d.reshape(1, nz, nz).expand(S, nz, nz)
-            B_d = B_d.reshape(1, nz, 1).expand(S, nz, 1)
-            C_d = C_d.reshape(1, n, nz).expand(S, n, nz)
-            shared = False
+        # A, B, C: one sharing mode for all three.  The kernels index every matrix with the same
+        # scenario offset, so a shared tensor is expanded as soon as any of them is per-scenario
+        # (or the loop updates the model online).
+        A_d = _as_model(A, (nz, nz), S, "A")
+        B_d = _as_model(B, (nz, 1), S, "B")
+        C_d = _as_model(C, (n, nz), S, "C")
+        shared = (not spec.update) and all(t.shape[0] == 1 for t in (A_d, B_d, C_d))
         self.shared_model = shared
-        self.A = A_d.reshape(-1, nz, nz).contiguous().clone()
-        self.B = B_d.reshape(-1, nz, 1).contiguous().clone()
-        self.C = C_d.reshape(-1, n, nz).contiguous().clone()
+        if not shared:
+            A_d, B_d, C_d = (t.expand(S, *t.shape[1:]) for t in (A_d, B_d, C_d))
+        self.A = A_d.contiguous().clone()
+        self.B = B_d.contiguous().clone()
+        self.C = C_d.contiguous().clone()
         r_d = to_dev(r)
         if r_d.ndim == 1:
             r_d = r_d.reshape(1, -1).expand(S, -1)
@@ -147,10 +172,15 @@ class ClosedLoop:
             _lib.check(L.kmpc_rbf_lift(ptr(self.x), ptr(self.cx), ptr(self.z), S, n, nz, spec.lift_mode,
                                        stream_ptr()))
         self.rls = None
+        self._rls0 = None            # warm start of construction, restored by reset()
         rls_started = 0
         if spec.update:
             if rls_state is not None:
-                self.rls, rls_started = rls_state, 1
+                _check_rls_state(rls_state, S, nz, n)
+                # the loop updates its OWN copy in place: the caller's warm state stays intact and
+                # reset() can start every episode from it
+                self.rls, rls_started = rls_state.clone(), 1
+                self._rls0 = rls_state.clone()
             else:
                 self.rls = RLSState(S, nz, n, spec.p0, spec.q0)
         # initial values kept for reset()
@@ -179,10 +209,12 @@ class ClosedLoop:
         """True when run(T) is ONE persistent fused kernel launch (nz = 8, N = 10 loops)."""
         return bool(_lib.lib().kmpc_ctx_is_fused(self._h))
 
-    def reset(self, x0=None, rls_state=None):
+    def reset(self, x0=None, rls_state=None, cold=False):
         """Start a new episode on the same device buffers (the reference's `for i in range(maxStep)`
         begins again): x <- x0 (default: the x0 of construction), z <- lift(x), u_prev <- 0,
-        A, B, C <- the initial model, step index <- 0, RLS restart pending again (or warm state)."""
+        A, B, C <- the initial model, step index <- 0.  RLS: a loop built with a warm `rls_state`
+        restarts from that same warm state (or from the `rls_state` given here); a loop built cold,
+        or `cold=True`, restarts from P = p0 I, bar_Q = q0 I (duffing.py:927-930)."""
         L = _lib.lib()
         spec = self.spec
         if x0 is not None:
@@ -199,10 +231,13 @@ class ClosedLoop:
             _lib.check(L.kmpc_rbf_lift(ptr(self.x), ptr(self.cx), ptr(self.z), self.S, spec.n, spec.nz,
                                        spec.lift_mode, stream_ptr()))
         started = 0
-        if spec.update and rls_state is not None:
-            for k in ("KA", "P", "barX", "barQ"):
-                getattr(self.rls, k).copy_(getattr(rls_state, k))
-            started = 1
+        if spec.update:
+            src = rls_state if rls_state is not None else (None if cold else self._rls0)
+            if src is not None:
+                _check_rls_state(src, self.S, spec.nz, spec.n)
+                for k in ("KA", "P", "barX", "barQ"):
+                    getattr(self.rls, k).copy_(getattr(src, k))
+                started = 1
         _lib.check(L.kmpc_ctx_reset(self._h, started, stream_ptr()))
         return self
 

@@ -115,6 +115,26 @@ static bool select_launch(const kmpc_loop_config& c, LoopLaunch* L) {
 
 using namespace kmpc;
 
+namespace {
+// CUDA events that are destroyed on every exit path (kmpc_closed_loop_steps_timed returns early on errors)
+struct EventList {
+  std::vector<cudaEvent_t> ev;
+  ~EventList() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+  cudaError_t create(size_t n) {
+    ev.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+      cudaEvent_t e;
+      const cudaError_t rc = cudaEventCreate(&e);
+      if (rc != cudaSuccess) return rc;
+      ev.push_back(e);
+    }
+    return cudaSuccess;
+  }
+};
+}  // namespace
+
 struct kmpc_ctx {
   LoopDev d;
   const kmpc_encoder* enc;
@@ -123,6 +143,8 @@ struct kmpc_ctx {
   LoopLaunch launch;
   bool fused;               // T steps per launch through fused_loop_kernel
   long long* d_timing;      // fused + timed: per-CTA phase cycle counters (allocated on first use)
+  cudaEvent_t ready;        // recorded after the memsets of create / reset; every run waits on it, so the
+                            // caller may create / reset on one stream and step on another
 };
 
 extern "C" {
@@ -162,6 +184,7 @@ int kmpc_ctx_create(kmpc_ctx** out, const kmpc_loop_config* cfg, const kmpc_loop
   ctx->d.z_next = nullptr;
   ctx->d.x_prev = nullptr;
   ctx->d_timing = nullptr;
+  ctx->ready = nullptr;
   ctx->d.wset = nullptr;
   ctx->d.qp_x = nullptr;
   ctx->fused = fused_eligible(ctx->d.c, enc);
@@ -177,9 +200,8 @@ int kmpc_ctx_create(kmpc_ctx** out, const kmpc_loop_config* cfg, const kmpc_loop
   }
   {
     // generic kernels: warm start from the previous step's optimal moves (0xFF bytes = NaN = none
-    // yet).  Debug knob: KMPC_QP_WARM=0 cold-starts every QP.
-    const char* e = getenv("KMPC_QP_WARM");
-    if (!ctx->fused && !(e && e[0] == '0')) {
+    // yet).  cfg.qp_cold = 1 cold-starts every QP (explicit per-context option).
+    if (!ctx->fused && !c.qp_cold) {
       if (cudaMalloc(&ctx->d.qp_x, (size_t)c.S * c.N * sizeof(double)) != cudaSuccess ||
           cudaMemsetAsync(ctx->d.qp_x, 0xFF, (size_t)c.S * c.N * sizeof(double), as_stream(stream)) != cudaSuccess) {
         kmpc_ctx_destroy(ctx);
@@ -197,12 +219,19 @@ int kmpc_ctx_create(kmpc_ctx** out, const kmpc_loop_config* cfg, const kmpc_loop
     kmpc_ctx_destroy(ctx);
     return KMPC_ERR_CUDA;
   }
+  if (cudaEventCreateWithFlags(&ctx->ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventRecord(ctx->ready, as_stream(stream)) != cudaSuccess) {
+    cudaGetLastError();
+    kmpc_ctx_destroy(ctx);
+    return KMPC_ERR_CUDA;
+  }
   *out = ctx;
   return KMPC_OK;
 }
 
 int kmpc_ctx_destroy(kmpc_ctx* ctx) {
   if (!ctx) return KMPC_OK;
+  if (ctx->ready) cudaEventDestroy(ctx->ready);
   if (ctx->d.z_next) cudaFree(ctx->d.z_next);
   if (ctx->d.x_prev) cudaFree(ctx->d.x_prev);
   if (ctx->d_timing) cudaFree(ctx->d_timing);
@@ -224,6 +253,7 @@ int kmpc_ctx_reset(kmpc_ctx* ctx, int rls_started, void* stream) {
     KMPC_CUDA(cudaMemsetAsync(ctx->d.wset, 0, (size_t)ctx->d.c.S * 2 * sizeof(unsigned int), as_stream(stream)));
   if (ctx->d.qp_x)
     KMPC_CUDA(cudaMemsetAsync(ctx->d.qp_x, 0xFF, (size_t)ctx->d.c.S * ctx->d.c.N * sizeof(double), as_stream(stream)));
+  KMPC_CUDA(cudaEventRecord(ctx->ready, as_stream(stream)));
   return KMPC_OK;
 }
 
@@ -272,6 +302,7 @@ static int run_fused(kmpc_ctx* ctx, int T, long long* timing, int* grid, void* s
 
 int kmpc_closed_loop_steps(kmpc_ctx* ctx, int T, void* stream) {
   if (!ctx || T < 0) return KMPC_ERR_ARG;
+  KMPC_CUDA(cudaStreamWaitEvent(as_stream(stream), ctx->ready, 0));
   if (ctx->fused) return run_fused(ctx, T, nullptr, nullptr, stream);
   for (int t = 0; t < T; ++t) {
     const int rc = run_one_step(ctx, stream, nullptr);
@@ -282,6 +313,7 @@ int kmpc_closed_loop_steps(kmpc_ctx* ctx, int T, void* stream) {
 
 int kmpc_closed_loop_steps_timed(kmpc_ctx* ctx, int T, void* stream, float* ms) {
   if (!ctx || T < 1 || !ms) return KMPC_ERR_ARG;
+  KMPC_CUDA(cudaStreamWaitEvent(as_stream(stream), ctx->ready, 0));
   if (ctx->fused) {
     // one launch; the kernel accumulates clock64() per phase in every CTA, the launch itself is
     // bracketed by CUDA events: ms[k] = launch time x mean over CTAs of the phase's cycle share
@@ -289,9 +321,9 @@ int kmpc_closed_loop_steps_timed(kmpc_ctx* ctx, int T, void* stream, float* ms) 
     if (!ctx->d_timing && cudaMalloc(&ctx->d_timing, sizeof(long long) * 4 * kMaxCtas) != cudaSuccess)
       return KMPC_ERR_ALLOC;
     cudaStream_t st = as_stream(stream);
-    cudaEvent_t e0, e1;
-    KMPC_CUDA(cudaEventCreate(&e0));
-    KMPC_CUDA(cudaEventCreate(&e1));
+    EventList el;
+    KMPC_CUDA(el.create(2));
+    const cudaEvent_t e0 = el.ev[0], e1 = el.ev[1];
     KMPC_CUDA(cudaEventRecord(e0, st));
     int grid = 0;
     int rc = run_fused(ctx, T, ctx->d_timing, &grid, stream);
@@ -308,6 +340,7 @@ int kmpc_closed_loop_steps_timed(kmpc_ctx* ctx, int T, void* stream, float* ms) 
       for (int i = 0; rc == KMPC_OK && i < grid; ++i)
         for (int k = 0; k < 3; ++k) share[k] += (double)h[4 * i + k] / (double)(h[4 * i + 3] > 0 ? h[4 * i + 3] : 1);
       for (int k = 0; k < 3; ++k) ms[k] = (float)(total * share[k] / (grid > 0 ? grid : 1));
+#ifdef KMPC_PROFILING
       if (rc == KMPC_OK && getenv("KMPC_DEBUG_TIMING")) {
         long long mx = 0, mn = h[3];
         double mean = 0.0;
@@ -320,17 +353,18 @@ int kmpc_closed_loop_steps_timed(kmpc_ctx* ctx, int T, void* stream, float* ms) 
         fprintf(stderr, "[kmpc] fused timed: grid %d, T %d, %.3f ms, CTA cycles min %lld mean %.0f max %lld -> SM clock %.0f MHz\n",
                 grid, T, total, mn, mean, mx, mx / (total * 1e3));
       }
+#endif
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return rc;
   }
   if (T > 1024) return KMPC_ERR_ARG;
-  std::vector<cudaEvent_t> ev((size_t)4 * T);
-  for (auto& e : ev) KMPC_CUDA(cudaEventCreate(&e));
+  EventList el;
+  KMPC_CUDA(el.create((size_t)4 * T));
+  std::vector<cudaEvent_t>& ev = el.ev;
   int rc = KMPC_OK;
   for (int t = 0; t < T && rc == KMPC_OK; ++t) rc = run_one_step(ctx, stream, ev.data() + 4 * t);
-  if (rc == KMPC_OK && cudaStreamSynchronize(as_stream(stream)) != cudaSuccess) rc = KMPC_ERR_CUDA;
+  // synchronise even after a failed step: the events recorded so far must not outlive their owner
+  if (cudaStreamSynchronize(as_stream(stream)) != cudaSuccess && rc == KMPC_OK) rc = KMPC_ERR_CUDA;
   ms[0] = ms[1] = ms[2] = 0.f;
   if (rc == KMPC_OK) {
     for (int t = 0; t < T; ++t)
@@ -340,7 +374,6 @@ int kmpc_closed_loop_steps_timed(kmpc_ctx* ctx, int T, void* stream, float* ms) 
         ms[k] += v;
       }
   }
-  for (auto& e : ev) cudaEventDestroy(e);
   return rc;
 }
 

@@ -5,6 +5,7 @@
 // Reference: duffing.py:21-29 (`nn.Sequential(Linear(2,100), ReLU, Linear(100,100), ReLU,
 // Linear(100,100), ReLU, Linear(100,8))`), Encoder_Tank.m:3-5 (3 layers, nz = 10).
 #pragma once
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -374,6 +375,13 @@ __device__ __forceinline__ void lift_unit(const EncParams& p, const double* in0,
 
 }  // namespace kmpc
 
+namespace kmpc {
+struct TcState;   // tc_lift.cu: split-precision weight image + tensor map of the tcgen05 lift
+TcState* tc_state_create(const double* const* W, const double* const* b, const int* dims, int n_layers,
+                         const double* d_z0, cudaStream_t st);
+void tc_state_destroy(TcState* t);
+}  // namespace kmpc
+
 // the opaque handle of include/kmpc.h
 struct kmpc_encoder {
   kmpc::EncParams p;
@@ -382,7 +390,13 @@ struct kmpc_encoder {
   int max_smem_optin = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin
   std::vector<double*> owned;
   double* d_z0 = nullptr;
-  // L2-resident lift workspace for kmpc_gram_from_snapshots (allocated on first use)
+  // L2-resident lift workspace of the fused lift + Gram entry points (allocated on first use).  One
+  // workspace per handle: calls on the same handle are serialised -- on the host by ws_mu (held while a
+  // call enqueues its work) and on the device by ws_done (recorded when a call's last kernel has been
+  // enqueued; the next call's stream waits on it), so two streams / threads never share its contents.
   double* d_ws = nullptr;
-  int64_t ws_rows = 0;
+  size_t ws_doubles = 0;
+  std::mutex ws_mu;
+  cudaEvent_t ws_done = nullptr;
+  kmpc::TcState* tc = nullptr;   // null: the net does not fit the tcgen05 kernel (KMPC_PREC_TC unsupported)
 };

@@ -397,9 +397,17 @@ struct FusedArgs {
   int first;          // 1: the first step restarts the RLS state (P = p0 I, bar_Q = q0 I)
   int64_t num_tiles;
   long long* timing;  // TIMED: [gridDim.x][4] cycles in QP+plant, lift, RLS, total
-  int dbg_skip;       // profiling aid (KMPC_FUSED_SKIP): bit 0 skip QP, bit 1 skip lift, bit 2 skip RLS,
-                      // bit 3 log the active-set iteration count in log_u instead of u
+#ifdef KMPC_PROFILING
+  int dbg_skip;       // profiling builds only (-DKMPC_PROFILING, env KMPC_FUSED_SKIP): bit 0 skip QP, bit 1 skip
+                      // lift, bit 2 skip RLS, bit 3 log the active-set iteration count in log_u instead of u
+#endif
 };
+// release builds have no phase-skip knob at all: the expression folds to 0
+#ifdef KMPC_PROFILING
+#define KMPC_DBG_SKIP(a) ((a).dbg_skip)
+#else
+#define KMPC_DBG_SKIP(a) 0
+#endif
 
 template <int OUT, bool UPDATE, bool MLP, bool TIMED>
 __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid_constant__ FusedArgs a) {
@@ -508,7 +516,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
       long long c0 = 0;
       if (TIMED) c0 = clock64();
       double x1n = x1, x2n = x2, unew = uprev;
-      if (!(a.dbg_skip & 1)) {
+      if (!(KMPC_DBG_SKIP(a) & 1)) {
       // ================= QP build: Krylov chains =================
       double VZ[FN], VB[FN];
       if (UPDATE) {
@@ -671,7 +679,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
               b.log_x[(slot * c.S + s) * 2] = x1n;
               b.log_x[(slot * c.S + s) * 2 + 1] = x2n;
             }
-            if (b.log_u && slot >= 0) b.log_u[slot * c.S + s] = (a.dbg_skip & 8) ? (double)qp.iters : unew;
+            if (b.log_u && slot >= 0) b.log_u[slot * c.S + s] = (KMPC_DBG_SKIP(a) & 8) ? (double)qp.iters : unew;
           }
         }
       }
@@ -688,7 +696,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
         if (l < 4) in0[act_index(l, sc & 7)] = (l == 0) ? x1n : ((l == 1) ? x2n : 0.0);
         quarter_barrier(qbar);
         if (TIMED) tq += clock64() - c0, c0 = clock64();
-        if (!(a.dbg_skip & 2))
+        if (!(KMPC_DBG_SKIP(a) & 2))
           lift_unit<2>(a.p, in0, region, region + a.sm.actbuf, yout, FNZ, wsm, wl ^ ((quarter >> 1) & 1), tid & 31, qbar);
         yl = yout[(sc & 7) * FNZ + l];
         if (c.lift_mode != KMPC_LIFT_RAW) yl -= a.p.z0[l];
@@ -700,7 +708,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
         if (TIMED) tl += clock64() - c0, c0 = clock64();
       }
       // ================= RLS (duffing.py:927-953, 965-984) =================
-      if (UPDATE && !(a.dbg_skip & 4)) {
+      if (UPDATE && !(KMPC_DBG_SKIP(a) & 4)) {
         double zv[8];
         group_gather(ex, l, zl, zv);
         const double u = unew;
@@ -857,10 +865,10 @@ static FusedKernel pick_fused(int out_mode, bool update, bool mlp) {
   return mlp ? fused_loop_kernel<KMPC_OUT_C, false, true, TIMED> : fused_loop_kernel<KMPC_OUT_C, false, false, TIMED>;
 }
 
-// Can the fused kernel run this loop?  (KMPC_FUSED=0 forces the generic three-kernel path.)
+// Can the fused kernel run this loop?  (cfg.path = KMPC_PATH_GENERIC forces the generic three-kernel
+// path: an explicit, per-context choice -- no environment variable is read on the launch path.)
 bool fused_eligible(const kmpc_loop_config& c, const kmpc_encoder* enc) {
-  const char* e = getenv("KMPC_FUSED");  // read per context so tests can compare both paths
-  if (e && e[0] == '0') return false;
+  if (c.path == KMPC_PATH_GENERIC) return false;
   if (c.nz != FNZ || c.N != FN || c.n != 2 || c.du_aug) return false;
   if (c.out_mode != KMPC_OUT_IDENTITY && c.out_mode != KMPC_OUT_C) return false;
   if (c.update && !(c.rls_flags & KMPC_RLS_UPDATE_C) && c.out_mode == KMPC_OUT_C) {
@@ -894,10 +902,12 @@ int fused_launch(const LoopDev& d, const kmpc_encoder* enc, int64_t step0, int T
   a.first = first;
   a.num_tiles = (c.S + kTileS - 1) / kTileS;
   a.timing = timing;
+#ifdef KMPC_PROFILING
   {
     const char* e = getenv("KMPC_FUSED_SKIP");
     a.dbg_skip = e ? atoi(e) : 0;
   }
+#endif
   int dev = 0, sms = 148;
   KMPC_CUDA(cudaGetDevice(&dev));
   KMPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

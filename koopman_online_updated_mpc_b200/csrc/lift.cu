@@ -267,6 +267,8 @@ encoder_kernel(EncParams p, const double* __restrict__ x, double* __restrict__ z
 }  // namespace kmpc
 
 namespace kmpc {
+int tc_encode_launch(const kmpc_encoder* enc, const double* x, double* z, int64_t S, int lift_mode,
+                     cudaStream_t st);   // tc_lift.cu
 int gram_accumulate_impl(const double* psi, const double* psi_next, const double* u, const double* x,
                          int64_t M, int nz, int n, double* pack, int seg, void* stream);   // edmd.cu
 
@@ -291,10 +293,14 @@ static int launch_encoder(const kmpc_encoder* enc, const double* x, double* z, i
   const int64_t tiles = (S + kTileS - 1) / kTileS;
   if (tiles > 0x7fffffff) return KMPC_ERR_ARG;
   const int out_dim = kmpc_encoder_out_dim(enc, lift_mode);
-  static const bool units_off = [] {   // debug knob: KMPC_ENC_UNITS=0 selects the CTA-wide kernel
+#ifdef KMPC_PROFILING
+  static const bool units_off = [] {   // profiling builds only: KMPC_ENC_UNITS=0 selects the CTA-wide kernel
     const char* e = getenv("KMPC_ENC_UNITS");
     return e && e[0] == '0';
   }();
+#else
+  constexpr bool units_off = false;
+#endif
   if (!units_off && units_eligible(enc->p, enc->max_smem_optin)) {
     const UnitsSmem L = units_smem_layout(enc->p);
     KMPC_CUDA(ensure_smem(encoder_units_kernel, L.total_bytes));
@@ -406,6 +412,9 @@ int kmpc_encoder_create(kmpc_encoder** out, const double* const* W, const double
   int rc = launch_encoder(enc, scratch, enc->d_z0, 1, KMPC_LIFT_RAW, st);
   if (rc != KMPC_OK) return fail(rc);
   if (cudaStreamSynchronize(st) != cudaSuccess) return fail(KMPC_ERR_CUDA);
+  // split-precision image for the tcgen05 lift (KMPC_PREC_TC); null when the net does not fit it
+  enc->tc = tc_state_create(W, b, dims, n_layers, enc->d_z0, st);
+  if (cudaEventCreateWithFlags(&enc->ws_done, cudaEventDisableTiming) != cudaSuccess) return fail(KMPC_ERR_CUDA);
   *out = enc;
   return KMPC_OK;
 }
@@ -414,6 +423,8 @@ int kmpc_encoder_destroy(kmpc_encoder* enc) {
   if (!enc) return KMPC_OK;
   for (double* p : enc->owned) cudaFree(p);
   if (enc->d_ws) cudaFree(enc->d_ws);
+  if (enc->ws_done) cudaEventDestroy(enc->ws_done);
+  tc_state_destroy(enc->tc);
   delete enc;
   return KMPC_OK;
 }
@@ -424,40 +435,83 @@ int kmpc_encoder_out_dim(const kmpc_encoder* enc, int lift_mode) {
   return lift_mode == KMPC_LIFT_STACK ? nz + enc->p.dims[0] : nz;
 }
 
-int kmpc_encode(const kmpc_encoder* enc, const double* x, double* z, int64_t S, int lift_mode,
-                void* stream) {
+static int encode_any(const kmpc_encoder* enc, const double* x, double* z, int64_t S, int lift_mode,
+                      int precision, cudaStream_t st) {
+  if (precision == KMPC_PREC_TC) return tc_encode_launch(enc, x, z, S, lift_mode, st);
+  return launch_encoder(enc, x, z, S, lift_mode, st);
+}
+
+int kmpc_encode_ex(const kmpc_encoder* enc, const double* x, double* z, int64_t S, int lift_mode,
+                   int precision, void* stream) {
   if (!enc || S < 0) return KMPC_ERR_ARG;
   if (lift_mode < KMPC_LIFT_RAW || lift_mode > KMPC_LIFT_STACK) return KMPC_ERR_ARG;
+  if (precision != KMPC_PREC_FP64 && precision != KMPC_PREC_TC) return KMPC_ERR_ARG;
+  if (precision == KMPC_PREC_TC && !enc->tc) return KMPC_ERR_UNSUPPORTED;
   if (S == 0) return KMPC_OK;
   if (!x || !z) return KMPC_ERR_ARG;
-  return launch_encoder(enc, x, z, S, lift_mode, as_stream(stream));
+  return encode_any(enc, x, z, S, lift_mode, precision, as_stream(stream));
 }
+
+int kmpc_encode(const kmpc_encoder* enc, const double* x, double* z, int64_t S, int lift_mode,
+                void* stream) {
+  return kmpc_encode_ex(enc, x, z, S, lift_mode, KMPC_PREC_FP64, stream);
+}
+
+int kmpc_encoder_has_tc(const kmpc_encoder* enc) { return (enc && enc->tc) ? 1 : 0; }
+
+// The lift workspace of a handle: sized from the actual widths, serialised across callers.
+namespace {
+constexpr int64_t kGramChunk = 1 << 18;   // 262144 rows: 2 x 16 MiB of lifted states at nz = 8 stay in L2
+struct WsLock {
+  kmpc_encoder* enc;
+  cudaStream_t st;
+  std::unique_lock<std::mutex> lk;
+  WsLock(kmpc_encoder* e, cudaStream_t s) : enc(e), st(s), lk(e->ws_mu) {}
+  // device-side order against the previous user of the workspace (possibly another stream)
+  cudaError_t acquire(size_t doubles) {
+    cudaError_t rc = cudaStreamWaitEvent(st, enc->ws_done, 0);
+    if (rc != cudaSuccess) return rc;
+    if (enc->ws_doubles < doubles) {
+      if (enc->d_ws) {
+        rc = cudaEventSynchronize(enc->ws_done);   // nobody may still be reading the old block
+        if (rc != cudaSuccess) return rc;
+        cudaFree(enc->d_ws);
+        enc->d_ws = nullptr;
+        enc->ws_doubles = 0;
+      }
+      rc = cudaMalloc(&enc->d_ws, doubles * sizeof(double));
+      if (rc != cudaSuccess) return rc;
+      enc->ws_doubles = doubles;
+    }
+    return cudaSuccess;
+  }
+  ~WsLock() { cudaEventRecord(enc->ws_done, st); }
+};
+}  // namespace
 
 // fused lift + Gram: lifts chunks of snapshots into an L2-sized workspace owned by the encoder
 // handle and accumulates the Gram pack from it, so PHIX / PHIY never round-trip HBM in full.
-int kmpc_gram_from_snapshots(const kmpc_encoder* enc_c, int lift_mode, const double* x,
-                             const double* y, const double* u, int64_t M, double* pack,
-                             void* stream) {
+int kmpc_gram_from_snapshots_ex(const kmpc_encoder* enc_c, int lift_mode, int precision, const double* x,
+                                const double* y, const double* u, int64_t M, double* pack,
+                                void* stream) {
   if (!enc_c || !x || !y || !u || !pack || M < 0) return KMPC_ERR_ARG;
+  if (precision != KMPC_PREC_FP64 && precision != KMPC_PREC_TC) return KMPC_ERR_ARG;
   kmpc_encoder* enc = const_cast<kmpc_encoder*>(enc_c);
+  if (precision == KMPC_PREC_TC && !enc->tc) return KMPC_ERR_UNSUPPORTED;
   const int nzo = kmpc_encoder_out_dim(enc, lift_mode);
   const int n = enc->p.dims[0];
-  const int64_t chunk = 1 << 18;  // 262144 snapshots: 2 * chunk * nz * 8 B = 32 MiB at nz = 8
-  if (!enc->d_ws || enc->ws_rows < chunk) {
-    if (enc->d_ws) cudaFree(enc->d_ws);
-    enc->d_ws = nullptr;
-    if (cudaMalloc(&enc->d_ws, (size_t)2 * chunk * (KMPC_MAX_NZ + 4) * sizeof(double)) != cudaSuccess)
-      return KMPC_ERR_ALLOC;
-    enc->ws_rows = chunk;
-  }
-  double* px = enc->d_ws;
-  double* py = enc->d_ws + (size_t)chunk * (KMPC_MAX_NZ + 4);
   if (nzo > KMPC_MAX_NZ) return KMPC_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  WsLock ws(enc, st);
+  const int64_t chunk = kGramChunk < M ? kGramChunk : (M > 0 ? M : 1);
+  if (ws.acquire((size_t)2 * chunk * nzo) != cudaSuccess) return KMPC_ERR_ALLOC;
+  double* px = enc->d_ws;
+  double* py = enc->d_ws + (size_t)chunk * nzo;
   for (int64_t m0 = 0; m0 < M; m0 += chunk) {
     const int64_t mc = (M - m0 < chunk) ? (M - m0) : chunk;
-    int rc = launch_encoder(enc, x + m0 * n, px, mc, lift_mode, as_stream(stream));
+    int rc = encode_any(enc, x + m0 * n, px, mc, lift_mode, precision, st);
     if (rc != KMPC_OK) return rc;
-    rc = launch_encoder(enc, y + m0 * n, py, mc, lift_mode, as_stream(stream));
+    rc = encode_any(enc, y + m0 * n, py, mc, lift_mode, precision, st);
     if (rc != KMPC_OK) return rc;
     rc = kmpc_gram_accumulate(px, py, u + m0, x + m0 * n, mc, nzo, n, pack, stream);
     if (rc != KMPC_OK) return rc;
@@ -465,42 +519,50 @@ int kmpc_gram_from_snapshots(const kmpc_encoder* enc_c, int lift_mode, const dou
   return KMPC_OK;
 }
 
+int kmpc_gram_from_snapshots(const kmpc_encoder* enc, int lift_mode, const double* x, const double* y,
+                             const double* u, int64_t M, double* pack, void* stream) {
+  return kmpc_gram_from_snapshots_ex(enc, lift_mode, KMPC_PREC_FP64, x, y, u, M, pack, stream);
+}
+
 // Trajectory-aware fused lift + Gram: the M = n_traj * n_step snapshots are trajectory-major and
 // CONSECUTIVE (y of snapshot j is x of snapshot j + 1 of the same trajectory, as data_generate.py
 // and kmpc_generate_snapshots produce them), so lift(y_j) == lift(x_{j+1}) bit for bit and every
 // state needs ONE encode: n_step + 1 per trajectory instead of 2 n_step.
-int kmpc_gram_from_trajectories(const kmpc_encoder* enc_c, int lift_mode, const double* x,
-                                const double* y, const double* u, int64_t n_traj, int n_step,
-                                double* pack, void* stream) {
+int kmpc_gram_from_trajectories_ex(const kmpc_encoder* enc_c, int lift_mode, int precision, const double* x,
+                                   const double* y, const double* u, int64_t n_traj, int n_step,
+                                   double* pack, void* stream) {
   if (!enc_c || !x || !y || !u || !pack || n_traj < 0 || n_step < 1) return KMPC_ERR_ARG;
+  if (precision != KMPC_PREC_FP64 && precision != KMPC_PREC_TC) return KMPC_ERR_ARG;
   kmpc_encoder* enc = const_cast<kmpc_encoder*>(enc_c);
+  if (precision == KMPC_PREC_TC && !enc->tc) return KMPC_ERR_UNSUPPORTED;
   const int nzo = kmpc_encoder_out_dim(enc, lift_mode);
   const int n = enc->p.dims[0];
   if (nzo > KMPC_MAX_NZ) return KMPC_ERR_UNSUPPORTED;
-  const int64_t chunk = 1 << 18;
-  if (n_step + 1 > chunk) return KMPC_ERR_UNSUPPORTED;
-  if (!enc->d_ws || enc->ws_rows < chunk) {
-    if (enc->d_ws) cudaFree(enc->d_ws);
-    enc->d_ws = nullptr;
-    if (cudaMalloc(&enc->d_ws, (size_t)2 * chunk * (KMPC_MAX_NZ + 4) * sizeof(double)) != cudaSuccess)
-      return KMPC_ERR_ALLOC;
-    enc->ws_rows = chunk;
-  }
-  double* pz = enc->d_ws;                                           // lifted rows (<= chunk x nz)
-  double* pin = enc->d_ws + (size_t)chunk * (KMPC_MAX_NZ + 4);      // gathered states (<= chunk x n)
-  const int64_t tc = chunk / (n_step + 1);                          // trajectories per chunk
+  if (n_step + 1 > kGramChunk) return KMPC_ERR_UNSUPPORTED;
+  int64_t tc = kGramChunk / (n_step + 1);                          // trajectories per chunk
+  if (tc > n_traj) tc = n_traj > 0 ? n_traj : 1;
+  const int64_t chunk_rows = tc * (n_step + 1);
   cudaStream_t st = as_stream(stream);
+  WsLock ws(enc, st);
+  if (ws.acquire((size_t)chunk_rows * (nzo + n)) != cudaSuccess) return KMPC_ERR_ALLOC;
+  double* pz = enc->d_ws;                                  // lifted rows (chunk_rows x nzo)
+  double* pin = enc->d_ws + (size_t)chunk_rows * nzo;      // gathered states (chunk_rows x n)
   for (int64_t t0 = 0; t0 < n_traj; t0 += tc) {
     const int64_t nt = (n_traj - t0 < tc) ? (n_traj - t0) : tc;
     const int64_t rows = nt * (n_step + 1), m0 = t0 * n_step;
     traj_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(x + m0 * n, y + m0 * n, n, nt, n_step, pin);
     KMPC_AFTER_LAUNCH();
-    int rc = launch_encoder(enc, pin, pz, rows, lift_mode, st);
+    int rc = encode_any(enc, pin, pz, rows, lift_mode, precision, st);
     if (rc != KMPC_OK) return rc;
     rc = gram_accumulate_impl(pz, nullptr, u + m0, x + m0 * n, nt * n_step, nzo, n, pack, n_step, stream);
     if (rc != KMPC_OK) return rc;
   }
   return KMPC_OK;
+}
+
+int kmpc_gram_from_trajectories(const kmpc_encoder* enc, int lift_mode, const double* x, const double* y,
+                                const double* u, int64_t n_traj, int n_step, double* pack, void* stream) {
+  return kmpc_gram_from_trajectories_ex(enc, lift_mode, KMPC_PREC_FP64, x, y, u, n_traj, n_step, pack, stream);
 }
 
 }  // extern "C"

@@ -27,20 +27,21 @@ def gram_accumulate(psi, psi_next, u, x, pack=None):
     return pack
 
 
-def gram_from_snapshots(encoder, x, y, u, pack=None, mode=None):
-    """Fused lift + Gram over raw snapshots x, y (M, n), u (M,)."""
+def gram_from_snapshots(encoder, x, y, u, pack=None, mode=None, precision=0):
+    """Fused lift + Gram over raw snapshots x, y (M, n), u (M,).  precision: lift.PREC_FP64 |
+    lift.PREC_TC (tcgen05 split-precision lift; the pack is accumulated in fp64 either way)."""
     x_d, y_d = to_dev(x), to_dev(y)
     u_d = to_dev(u).reshape(-1)
     mode = encoder.mode if mode is None else mode
     nz = encoder.out_dim(mode)
     if pack is None:
         pack = torch.zeros(gram_pack_len(nz, x_d.shape[1]), dtype=torch.float64, device=x_d.device)
-    _lib.check(_lib.lib().kmpc_gram_from_snapshots(encoder.handle, mode, ptr(x_d), ptr(y_d), ptr(u_d),
-                                                   x_d.shape[0], ptr(pack), stream_ptr()))
+    _lib.check(_lib.lib().kmpc_gram_from_snapshots_ex(encoder.handle, mode, int(precision), ptr(x_d), ptr(y_d),
+                                                      ptr(u_d), x_d.shape[0], ptr(pack), stream_ptr()))
     return pack
 
 
-def gram_from_trajectories(encoder, x, y, u, n_step, pack=None, mode=None, verify=False):
+def gram_from_trajectories(encoder, x, y, u, n_step, pack=None, mode=None, verify=False, precision=0):
     """Fused lift + Gram over CONSECUTIVE trajectory-major snapshots (what data_generate.py:63-74
     returns: y of snapshot j is x of snapshot j + 1 of the same trajectory): every state is lifted
     once, n_step + 1 encodes per trajectory instead of 2 n_step.  `verify=True` checks the
@@ -58,8 +59,9 @@ def gram_from_trajectories(encoder, x, y, u, n_step, pack=None, mode=None, verif
     nz = encoder.out_dim(mode)
     if pack is None:
         pack = torch.zeros(gram_pack_len(nz, n), dtype=torch.float64, device=x_d.device)
-    _lib.check(_lib.lib().kmpc_gram_from_trajectories(encoder.handle, mode, ptr(x_d), ptr(y_d), ptr(u_d),
-                                                      M // n_step, int(n_step), ptr(pack), stream_ptr()))
+    _lib.check(_lib.lib().kmpc_gram_from_trajectories_ex(encoder.handle, mode, int(precision), ptr(x_d), ptr(y_d),
+                                                         ptr(u_d), M // n_step, int(n_step), ptr(pack),
+                                                         stream_ptr()))
     return pack
 
 

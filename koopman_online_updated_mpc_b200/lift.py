@@ -11,6 +11,7 @@ from .weights import load_encoder_weights
 
 LIFT_RAW, LIFT_OFFSET, LIFT_STACK = 0, 1, 2
 RBF_PYTHON, RBF_MATLAB = 0, 1
+PREC_FP64, PREC_TC = 0, 1   # include/kmpc.h KMPC_PREC_*: fp64 DMMA path | tcgen05 bf16x3 split path (~1e-7)
 
 
 class Encoder:
@@ -52,18 +53,23 @@ class Encoder:
     def out_dim(self, mode=None):
         return int(_lib.lib().kmpc_encoder_out_dim(self._h, self.mode if mode is None else mode))
 
-    def encode_into(self, x_dev, z_dev, mode=None):
+    @property
+    def has_tc(self):
+        """True when the net fits the tcgen05 split-precision kernel (PREC_TC)."""
+        return bool(_lib.lib().kmpc_encoder_has_tc(self._h))
+
+    def encode_into(self, x_dev, z_dev, mode=None, precision=PREC_FP64):
         """Zero-copy form: x_dev (S, n), z_dev (S, out_dim) CUDA float64 tensors."""
         S = x_dev.shape[0]
-        _lib.check(_lib.lib().kmpc_encode(self._h, ptr(x_dev), ptr(z_dev), S,
-                                          self.mode if mode is None else mode, stream_ptr()))
+        _lib.check(_lib.lib().kmpc_encode_ex(self._h, ptr(x_dev), ptr(z_dev), S,
+                                             self.mode if mode is None else mode, int(precision), stream_ptr()))
         return z_dev
 
-    def __call__(self, x, mode=None):
+    def __call__(self, x, mode=None, precision=PREC_FP64):
         single = (x.ndim == 1)
         xd = to_dev(x).reshape(-1, self.n)
         z = torch.empty((xd.shape[0], self.out_dim(mode)), dtype=torch.float64, device=xd.device)
-        self.encode_into(xd, z, mode)
+        self.encode_into(xd, z, mode, precision)
         if single:
             z = z[0]
         return like_input(z, x)

@@ -20,17 +20,44 @@ def mpc_first_move(A, B, C, z0, r, lb, ub, N=10, q=100.0, rw=1e-4, PN=None, retu
     if z0_d.ndim == 1:
         z0_d = z0_d.reshape(1, -1)
     S, nz = z0_d.shape
-    A_d = to_dev(A)
     flags = 0
-    if A_d.ndim == 2:
-        flags |= QP_SHARED_MODEL
-    B_d = to_dev(B).reshape(-1, nz) if A_d.ndim == 3 else to_dev(B).reshape(nz)
     if C is None:
         flags |= QP_CY_IDENTITY
-        C_d, ny = None, nz
+        ny = nz
     else:
-        C_d = to_dev(C)
-        ny = C_d.shape[-2]
+        C_t = to_dev(C)
+        if C_t.ndim < 2 or C_t.shape[-1] != nz:
+            raise ValueError("C has shape %s: expected (ny, %d) or (S, ny, %d)" % (tuple(C_t.shape), nz, nz))
+        ny = C_t.shape[-2]
+
+    def model(M, tail, name):
+        """(tail) shared or (S, tail) per scenario -> (1|S, *tail)"""
+        t = to_dev(M)
+        numel = 1
+        for d in tail:
+            numel *= d
+        if t.numel() == numel:
+            return t.reshape(1, *tail)
+        if t.numel() == S * numel and t.shape[0] == S:
+            return t.reshape(S, *tail)
+        raise ValueError("%s has shape %s: expected %s or (%d, ...)" % (name, tuple(t.shape), tail, S))
+    # A, B, C, PN: ONE sharing mode.  The kernel indexes all of them with the same scenario offset,
+    # so a shared matrix is expanded as soon as any other is per-scenario.
+    mats = {"A": model(A, (nz, nz), "A"), "B": model(B, (nz,), "B")}
+    if C is not None:
+        mats["C"] = model(C, (ny, nz), "C")
+    if PN is not None:
+        mats["PN"] = model(PN, (ny, ny), "PN")
+    if all(t.shape[0] == 1 for t in mats.values()):
+        flags |= QP_SHARED_MODEL
+    else:
+        mats = {k: t.expand(S, *t.shape[1:]).contiguous() for k, t in mats.items()}
+    A_d, B_d = mats["A"].contiguous(), mats["B"].contiguous()
+    C_d, PN_d = mats.get("C"), mats.get("PN")
+    if C_d is not None:
+        C_d = C_d.contiguous()
+    if PN_d is not None:
+        PN_d = PN_d.contiguous()
     r_d = to_dev(r)
     if r_d.ndim == 1:
         r_d = r_d.reshape(1, -1).expand(S, -1).contiguous()
@@ -45,9 +72,14 @@ def mpc_first_move(A, B, C, z0, r, lb, ub, N=10, q=100.0, rw=1e-4, PN=None, retu
         if isinstance(b, (int, float)):
             return torch.full((S, N), float(b), dtype=torch.float64, device=dev)
         t = to_dev(b)
-        return t.reshape(1, -1).expand(S, N).contiguous() if t.ndim == 1 else t
+        if t.ndim <= 1:
+            if t.numel() not in (1, N):
+                raise ValueError("bound has %d entries: expected a scalar, (N,) or (S, N)" % t.numel())
+            return t.reshape(1, -1).expand(S, N).contiguous()
+        if tuple(t.shape) != (S, N):
+            raise ValueError("bound has shape %s: expected (%d, %d)" % (tuple(t.shape), S, N))
+        return t
     lb_d, ub_d = bound(lb), bound(ub)
-    PN_d = None if PN is None else to_dev(PN)
     u0 = torch.empty(S, dtype=torch.float64, device=dev)
     U = torch.empty((S, N), dtype=torch.float64, device=dev) if return_sequence else None
     status = torch.zeros(S, dtype=torch.int32, device=dev)

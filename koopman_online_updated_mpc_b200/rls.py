@@ -42,6 +42,14 @@ class RLSState:
         st.barQ = torch.tensor(np.linalg.pinv(PsiPsi), **f64).repeat(S, 1, 1).contiguous()
         return st
 
+    def clone(self):
+        """Deep copy (same device)."""
+        c = object.__new__(RLSState)
+        c.S, c.nz, c.n = self.S, self.nz, self.n
+        for k in ("KA", "P", "barX", "barQ", "A", "B", "C"):
+            setattr(c, k, getattr(self, k).clone())
+        return c
+
     def state_dict(self):
         return {k: getattr(self, k) for k in ("KA", "P", "barX", "barQ", "A", "B", "C")}
 

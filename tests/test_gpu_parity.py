@@ -1,5 +1,7 @@
 """Parity tests proper: the sm_100a kernels, called through the C ABI (ctypes -> libkmpc.so),
 against the oracle and the reference goldens.  Run on the B200 box with `-m gpu`."""
+from dataclasses import replace
+
 import numpy as np
 import pytest
 import torch
@@ -283,14 +285,14 @@ def test_launch_counter_counts_kernels():
 # ------------------------------------------------------------------------------ fused kernel ---
 @pytest.mark.parametrize("name,T", [("duffing", 150), ("duffing_frozen", 130), ("vdp", 150), ("vdp_frozen", 110),
                                     ("duffing_rbf_frozen", 110)])
-def test_fused_kernel_matches_generic_three_kernel_path(name, T, monkeypatch):
+def test_fused_kernel_matches_generic_three_kernel_path(name, T):
     """The persistent fused kernel (fused.cu: state in registers, T steps per launch) against the
     generic qp_plant -> lift -> rls kernels (closed_loop.cu) on the same scenarios."""
     case = cases.loop_case(name)
     fused = _run_cuda(case, T)
-    monkeypatch.setenv("KMPC_FUSED", "0")
-    generic = _run_cuda(case, T)
-    monkeypatch.delenv("KMPC_FUSED")
+    assert fused["loop"].fused
+    generic = _run_cuda(dict(case, spec=replace(case["spec"], path=K.closed_loop.PATH_GENERIC)), T)
+    assert not generic["loop"].fused
     assert np.array_equal(fused["status"], generic["status"])
     # same bar as against the oracle (cases.loop_tolerances): the RLS restart makes the first steps
     # of the update loops amplify rounding differences between the two arithmetic orders
