@@ -47,8 +47,7 @@ constexpr int kTcAccCol = 0, kTcACol0 = 128, kTcAColStride = 192, kTcCols = 512;
 
 struct TcDev {   // kernel argument (by value)
   int n_in, d1, n_gemm, out;
-  const double* w1;        // [d1][n_in] fp64 (nn.Linear layout)
-  const double* b1;        // [d1]
+  const double* w1;        // [NP][6] fp64: layer-0 rows (w0 w1 w2 w3 bias 0), zero rows beyond d1
   const float* bias_h;     // [n_gemm][NP] fp32, zero padded
   const double* bias_o;    // [16] fp64, zero padded
   const double* z0;        // theta(0) from the fp64 path (OFFSET / STACK modes)
@@ -56,16 +55,15 @@ struct TcDev {   // kernel argument (by value)
 };
 
 struct TcSmem {
-  int w, w1, b1, bias_h, bias_o, bars, tmem, total;
+  int w, w1, bias_h, bias_o, bars, tmem, total;
 };
-__host__ __device__ inline TcSmem tc_smem_layout(int n_gemm, int d1, int n_in) {
+constexpr int kTcW1Row = 6;   // layer-0 table row: w[0..3] (zero padded), bias, pad -- 48 B, three 16-byte loads
+__host__ __device__ inline TcSmem tc_smem_layout(int n_gemm) {
   TcSmem L;
   L.w = 0;
   int o = n_gemm * 3 * kTcPieceBytes + 3 * kTcLastPieceBytes;
   L.w1 = o;
-  o += d1 * n_in * 8;
-  L.b1 = o;
-  o += d1 * 8;
+  o += kTcNP * kTcW1Row * 8;
   L.bias_o = o;
   o += 16 * 8;
   L.bias_h = o;
@@ -114,31 +112,39 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 // D[tmem] (+)= A[tmem] . B[smem desc]^T, kind::f16 (bf16 operands, fp32 accumulate), one CTA
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                        uint32_t accumulate) {
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t b_desc_hi,
+                                        uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      ".reg .b64 bd;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 bd, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n"
       "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// one lane of a converged warp (SASS ELECT): the issuer of the warp's tcgen05.mma / TMA instructions
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-// K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO), LBO unused, descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;                 // leading byte offset (ignored for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
-  d |= (uint64_t)1 << 46;                 // version
-  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
-  return d;
-}
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO), LBO
+// unused, descriptor version 1 (sm_100).  Low word: start address >> 4 | LBO; high word: constant.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
 // bf16 x bf16 -> f32, A and B K-major, M = 128
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
@@ -175,14 +181,14 @@ __device__ __forceinline__ void store_a_chunk(uint32_t a_lane_base, int ch, cons
   tmem_st8(a_lane_base + 2 * (kTcNP / 2) + ch * 8, w2);
 }
 
+template <int NIN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_encoder_kernel(const __grid_constant__ CUtensorMap wmap, const TcDev p, const double* __restrict__ x,
                   double* __restrict__ z, int64_t S, int lift_mode, int out_dim, int64_t n_pairs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned (128 B swizzle atoms)
-  const TcSmem L = tc_smem_layout(p.n_gemm, p.d1, p.n_in);
+  const TcSmem L = tc_smem_layout(p.n_gemm);
   double* w1s = reinterpret_cast<double*>(smem + L.w1);
-  double* b1s = reinterpret_cast<double*>(smem + L.b1);
   double* bos = reinterpret_cast<double*>(smem + L.bias_o);
   float* bhs = reinterpret_cast<float*>(smem + L.bias_h);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -202,8 +208,7 @@ tc_encoder_kernel(const __grid_constant__ CUtensorMap wmap, const TcDev p, const
     mbar_init(acc_free, 128);
     mbar_fence_init();
   }
-  for (int e = tid; e < p.d1 * p.n_in; e += kTcThreads) w1s[e] = p.w1[e];
-  for (int e = tid; e < p.d1; e += kTcThreads) b1s[e] = p.b1[e];
+  for (int e = tid; e < kTcNP * kTcW1Row; e += kTcThreads) w1s[e] = p.w1[e];
   for (int e = tid; e < 16; e += kTcThreads) bos[e] = p.bias_o[e];
   for (int e = tid; e < p.n_gemm * kTcNP; e += kTcThreads) bhs[e] = p.bias_h[e];
   if (warp == 8) {   // TMEM: all 512 columns (one CTA per SM: the weight image fills shared memory)
@@ -236,8 +241,9 @@ tc_encoder_kernel(const __grid_constant__ CUtensorMap wmap, const TcDev p, const
                       kb * 64, row, wbar);
     }
     mbar_wait_bounded(wbar, 0);
-    const uint32_t w_base = smem_u32(smem + L.w);
+    const uint32_t w_lo = umma_desc_lo(smem_u32(smem + L.w));   // descriptor of the first weight byte
     const uint32_t idesc_h = umma_idesc_bf16(kTcNP), idesc_o = umma_idesc_bf16(kTcNLast);
+    const bool leader = elect_one();
     uint32_t n_batch = 0, ready_cnt[2] = {0, 0};
     for (int64_t it = 0; it < my_iters; ++it) {
       for (int j = 0; j < n_batches; ++j) {
@@ -247,22 +253,34 @@ tc_encoder_kernel(const __grid_constant__ CUtensorMap wmap, const TcDev p, const
           if (n_batch > 0) mbar_wait_bounded(acc_free, (n_batch - 1) & 1);
           ++n_batch;
           tc_fence_after();
-          if (lane == 0) {
-            const bool last = (j == p.n_gemm);
-            const uint32_t wl = last ? w_base + p.n_gemm * 3 * kTcPieceBytes : w_base + j * 3 * kTcPieceBytes;
-            const uint32_t piece = last ? kTcLastPieceBytes : kTcPieceBytes;
-            const uint32_t blk = last ? kTcLastBlkBytes : kTcBlkBytes;
-            const uint32_t idesc = last ? idesc_o : idesc_h;
+          if (leader) {
             const uint32_t a_base = tmem_base + kTcACol0 + slot * kTcAColStride;
-            // order-2 products first, the dominant a0.b0 last (see the header)
+            const uint32_t acc = tmem_base + kTcAccCol;
+            // order-2 products first, the dominant a0.b0 last (see the header); every descriptor is
+            // the layer's base plus a compile-time offset (16-byte units)
+            if (j < p.n_gemm) {
+              const uint32_t wl = w_lo + (uint32_t)j * (3 * kTcPieceBytes >> 4);
 #pragma unroll
-            for (int t = 0; t < 6; ++t) {
-              const int pa = (t == 0) ? 2 : ((t == 1 || t == 3) ? 1 : 0);
-              const int pb = (t == 2) ? 2 : ((t == 1 || t == 4) ? 1 : 0);
+              for (int t = 0; t < 6; ++t) {
+                const int pa = (t == 0) ? 2 : ((t == 1 || t == 3) ? 1 : 0);
+                const int pb = (t == 2) ? 2 : ((t == 1 || t == 4) ? 1 : 0);
 #pragma unroll
-              for (int ks = 0; ks < kTcKS; ++ks) {
-                const uint64_t bd = umma_desc_sw128(wl + pb * piece + (ks >> 2) * blk + (ks & 3) * 32);
-                umma_ts(tmem_base + kTcAccCol, a_base + pa * (kTcNP / 2) + ks * 8, bd, idesc, (t | ks) ? 1u : 0u);
+                for (int ks = 0; ks < kTcKS; ++ks)
+                  umma_ts(acc, a_base + pa * (kTcNP / 2) + ks * 8,
+                          wl + ((pb * kTcPieceBytes + (ks >> 2) * kTcBlkBytes + (ks & 3) * 32) >> 4), kDescHiSw128,
+                          idesc_h, (t | ks) ? 1u : 0u);
+              }
+            } else {
+              const uint32_t wl = w_lo + (uint32_t)p.n_gemm * (3 * kTcPieceBytes >> 4);
+#pragma unroll
+              for (int t = 0; t < 6; ++t) {
+                const int pa = (t == 0) ? 2 : ((t == 1 || t == 3) ? 1 : 0);
+                const int pb = (t == 2) ? 2 : ((t == 1 || t == 4) ? 1 : 0);
+#pragma unroll
+                for (int ks = 0; ks < kTcKS; ++ks)
+                  umma_ts(acc, a_base + pa * (kTcNP / 2) + ks * 8,
+                          wl + ((pb * kTcLastPieceBytes + (ks >> 2) * kTcLastBlkBytes + (ks & 3) * 32) >> 4),
+                          kDescHiSw128, idesc_o, (t | ks) ? 1u : 0u);
               }
             }
             umma_commit(&acc_full[slot]);
@@ -287,27 +305,29 @@ tc_encoder_kernel(const __grid_constant__ CUtensorMap wmap, const TcDev p, const
       double xin[4] = {0.0, 0.0, 0.0, 0.0};
       if (valid) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < NIN; ++k)
           if (k < n) {
             xin[k] = x[row * n + k];
             if (lift_mode == KMPC_LIFT_STACK) z[row * out_dim + k] = xin[k];
           }
       }
+      // branch-free: the table is zero beyond d1 / n_in, so padded outputs come out as relu(0) = 0
 #pragma unroll 1
       for (int ch = 0; ch < kTcKS; ++ch) {
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int o = ch * 16 + i;
-          double h = 0.0;
-          if (o < p.d1) {
-            h = b1s[o];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < n) h = fma(w1s[o * n + k], xin[k], h);
-            h = relu_nan(h);
+          const double2* wr = reinterpret_cast<const double2*>(w1s + (ch * 16 + i) * kTcW1Row);
+          const double2 w01 = wr[0], bb = wr[2];
+          double h = fma(w01.x, xin[0], bb.x);
+          h = fma(w01.y, xin[1], h);
+          if (NIN > 2) {
+            const double2 w23 = wr[1];
+            h = fma(w23.x, xin[2], h);
+            h = fma(w23.y, xin[3], h);
           }
-          v[i] = (float)h;
+          const float f = (float)h;
+          v[i] = f < 0.f ? 0.f : f;   // NaN-propagating ReLU (rounding and ReLU commute)
         }
         store_a_chunk(a_lane_base, ch, v);
       }
@@ -448,13 +468,15 @@ TcState* tc_state_create(const double* const* W, const double* const* b, const i
   };
   for (int g = 0; g < n_gemm; ++g) put(g * 3 * kTcNP, kTcNP, W[g + 1], dims[g + 2], dims[g + 1]);
   put(n_gemm * 3 * kTcNP, kTcNLast, W[n_layers - 1], out, dims[n_layers - 1]);
-  // misc block: w1 [d1][n_in] f64 | b1 [d1] f64 | bias_o [16] f64 | bias_h [n_gemm][NP] f32
-  const size_t n_w1 = (size_t)d1 * n_in, misc_d = n_w1 + d1 + 16;
+  // misc block: layer-0 table [NP][6] f64 | bias_o [16] f64 | bias_h [n_gemm][NP] f32
+  const size_t n_w1 = (size_t)kTcNP * kTcW1Row, misc_d = n_w1 + 16;
   std::vector<double> md(misc_d, 0.0);
   std::vector<float> mf((size_t)(n_gemm > 0 ? n_gemm : 1) * kTcNP, 0.f);
-  for (size_t e = 0; e < n_w1; ++e) md[e] = W[0][e];
-  for (int o = 0; o < d1; ++o) md[n_w1 + o] = b[0][o];
-  for (int o = 0; o < out; ++o) md[n_w1 + d1 + o] = b[n_layers - 1][o];
+  for (int o = 0; o < d1; ++o) {
+    for (int k = 0; k < n_in; ++k) md[(size_t)o * kTcW1Row + k] = W[0][(size_t)o * n_in + k];
+    md[(size_t)o * kTcW1Row + 4] = b[0][o];
+  }
+  for (int o = 0; o < out; ++o) md[n_w1 + o] = b[n_layers - 1][o];
   for (int g = 0; g < n_gemm; ++g)
     for (int o = 0; o < dims[g + 2]; ++o) mf[(size_t)g * kTcNP + o] = (float)b[g + 1][o];
   TcState* t = new TcState();
@@ -483,17 +505,17 @@ TcState* tc_state_create(const double* const* W, const double* const* b, const i
   t->dev.out = out;
   const double* dm = reinterpret_cast<const double*>(t->d_misc);
   t->dev.w1 = dm;
-  t->dev.b1 = dm + n_w1;
-  t->dev.bias_o = dm + n_w1 + d1;
+  t->dev.bias_o = dm + n_w1;
   t->dev.bias_h = reinterpret_cast<const float*>(dm + misc_d);
   t->dev.z0 = d_z0;
   t->dev.w_bytes = (uint32_t)(n_gemm * 3 * kTcPieceBytes + 3 * kTcLastPieceBytes);
-  t->smem_bytes = tc_smem_layout(n_gemm, d1, n_in).total;
+  t->smem_bytes = tc_smem_layout(n_gemm).total;
   int dev = 0, max_smem = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (t->smem_bytes > max_smem) return fail();
-  if (cudaFuncSetAttribute(tc_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_bytes) != cudaSuccess)
+  if (cudaFuncSetAttribute(tc_encoder_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_bytes) != cudaSuccess ||
+      cudaFuncSetAttribute(tc_encoder_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_bytes) != cudaSuccess)
     return fail();
   t->ok = true;
   return t;
@@ -505,7 +527,10 @@ int tc_encode_launch(const kmpc_encoder* enc, const double* x, double* z, int64_
   const int64_t tiles = (S + kTcRows - 1) / kTcRows, pairs = (tiles + 1) / 2;
   const unsigned grid = (unsigned)(pairs < enc->num_sms ? pairs : enc->num_sms);
   const int out_dim = kmpc_encoder_out_dim(enc, lift_mode);
-  tc_encoder_kernel<<<grid, kTcThreads, t->smem_bytes, st>>>(t->wmap, t->dev, x, z, S, lift_mode, out_dim, pairs);
+  if (t->dev.n_in <= 2)
+    tc_encoder_kernel<2><<<grid, kTcThreads, t->smem_bytes, st>>>(t->wmap, t->dev, x, z, S, lift_mode, out_dim, pairs);
+  else
+    tc_encoder_kernel<4><<<grid, kTcThreads, t->smem_bytes, st>>>(t->wmap, t->dev, x, z, S, lift_mode, out_dim, pairs);
   KMPC_AFTER_LAUNCH();
   return KMPC_OK;
 }

@@ -86,6 +86,32 @@ def tank_config(lift_fn, nz):
                       skip_first_barx=True)
 
 
+def koopman_update_config(Ws, bs, lam=1.0):
+    """Revise_2/Koopman_update.m: lift [x; theta(x)] - [0; theta(0)] (nz = 10, l.67-70), Cy = I_2 on the
+    jointly regressed C (l.94-101, 108), N = 10, Q = 10 I_2, R = 0.01 (l.110-113), bounds +-2 (l.213),
+    MATLAB RK4 with k4 = f(x + k1 dt) (l.21-25), RLS with forgetting factor `lambda` (= 1.0 in the
+    file, l.257) warm-started from the offline Gram (l.264-265), C never updated.  Steps = 100
+    (l.154) so the `i > 100` plant switch (l.230-239) never fires: first_post_step is out of reach.
+    The SDP terminal weight (l.314-381) is out of scope."""
+    return LoopConfig("koopman_update", lambda x: lift.lift_mlp(Ws, bs, x, lift.LIFT_STACK), 10,
+                      p_pre=plant.DUFFING_PRE, p_post=plant.DUFFING_POST, first_post_step=1 << 30,
+                      rk4_variant=plant.RK4_MATLAB, N=10, q=10.0, rw=0.01, lb=-2.0, ub=2.0,
+                      r=np.array([1.0, 0.0]), lam=lam, update_c=False)
+
+
+def tracking_lift_config(Ws, bs, xref=(-1.0, 0.0)):
+    """VDP_Revise_2/Koopman_update_Tracking_Lift.m: lift theta(x) - theta(0) (l.65), C = I (l.99: the
+    cost tracks the lifted reference Yr = liftFun([-1; 0]), l.109), N = 10, Q = 100 I_8, R = 1e-4
+    (l.106-108), bounds +-6 (l.151), RLS restart P0 = pinv(1e-5 I) (l.183-185), C never updated,
+    MATLAB RK4 (l.21-25), plant switch tested BEFORE the plant call with 1-based i (l.157-165):
+    first new-plant step is 0-based k = 100."""
+    f = lambda x: lift.lift_mlp(Ws, bs, x, lift.LIFT_OFFSET)
+    return LoopConfig("tracking_lift", f, 8, p_pre=plant.VDP_PRE, p_post=plant.VDP_POST, first_post_step=100,
+                      rk4_variant=plant.RK4_MATLAB, N=10, q=100.0, rw=1e-4, lb=-6.0, ub=6.0,
+                      out_mode=OUT_IDENTITY, r=f(np.asarray(xref, dtype=np.float64)), p0=1e5, q0=1e5,
+                      update_c=False)
+
+
 def qp_model(cfg, A, B, C):
     """Matrices the QP sees: optional du-augmentation and the output selection."""
     A = np.asarray(A, dtype=np.float64)

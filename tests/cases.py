@@ -231,3 +231,31 @@ def compare_teacher_forced(got, want):
     for k in ("A", "B", "C"):
         scale = np.abs(want[k]).reshape(len(want[k]), -1).max(axis=1).reshape((-1,) + (1,) * (want[k].ndim - 1))
         assert np.all(np.abs(got[k].reshape(want[k].shape) - want[k]) <= 1e-6 * np.maximum(scale, 1e-3)), k
+
+
+# ------------------------------------------------------------------------------ MATLAB scripts --
+def matlab_offline(system, seed=2141444, n_traj=100, n_step=100):
+    """Offline identification of the two `Koopman_update*.m` scripts, restated with the oracle:
+    data collection with the MATLAB RK4 (Koopman_update.m:32-49, Tracking_Lift.m:26-47; numpy
+    RandomState(seed) stands in for MATLAB's unseeded `rand`: the draws are inputs), lifting
+    (Koopman_update.m:67, Tracking_Lift.m:65), joint Gram regression (l.94-101 / l.88-99)."""
+    Ws, bs = H.oracle_weights("duffing" if system == "koopman_update" else "vdp")
+    p = oplant.DUFFING_PRE if system == "koopman_update" else oplant.VDP_PRE
+    rs = np.random.RandomState(seed)
+    u0 = 4 * rs.rand(n_step, n_traj) - 2
+    x = 4 * rs.rand(n_traj, 2) - 2
+    Xs, Ys = [], []
+    for i in range(n_step):
+        xn = oplant.rk4_step(x, u0[i], np.asarray(p), 0.05, oplant.RK4_MATLAB)
+        Xs.append(x), Ys.append(xn)
+        x = xn
+    X = np.stack(Xs, axis=1).reshape(n_traj * n_step, 2).T          # trajectory-major like the GPU generator
+    Y = np.stack(Ys, axis=1).reshape(n_traj * n_step, 2).T
+    U = u0.T.reshape(1, n_traj * n_step)
+    mode = olift.LIFT_STACK if system == "koopman_update" else olift.LIFT_OFFSET
+    PX, PY = olift.lift_mlp(Ws, bs, X.T, mode).T, olift.lift_mlp(Ws, bs, Y.T, mode).T
+    G, Aq, XV = oedmd.gram_pack(PX, PY, U, X)
+    nz = PX.shape[0]
+    A, B, C = oedmd.edmd_from_gram(G, Aq, XV, nz, oedmd.C_JOINT)
+    cfg = ocl.koopman_update_config(Ws, bs) if system == "koopman_update" else ocl.tracking_lift_config(Ws, bs)
+    return dict(Ws=Ws, bs=bs, X=X, Y=Y, U=U, G=G, Aq=Aq, XV=XV, A=A, B=B, C=C, cfg=cfg, nz=nz, u0=u0, seed=seed)
