@@ -294,10 +294,12 @@ def secondary_workloads(K, D, dev, rank, world, dmma_peak, hbm_peak, bf16_peak):
     x0 = np.maximum(np.random.default_rng(20240801).uniform(0, 2, (S_total, 2)), 0.0)[lo:hi]
     loop = K.ClosedLoop(K.tank_spec(), x0, At, Bt, Ct, np.array([1.0]), encoder=enc_t, log_steps=T)
     ms = time_loop(loop, T, 1)
-    # 2(22.4 k theta_E) is not needed: one encode per step (y_k = z_{k+1}); QP build N = 20 ~ 25 k, RLS 4 k
+    # algorithmic flops per scenario-step: theta_E 2-100-100-10 22.6 k, Krylov chains 20 x 2 x 11^2
+    # 4.8 k, H and f 0.9 k, ONE 20 x 20 Cholesky + two triangular solves 3.5 k, RLS (11 x 11 P, 10 x 10 bar_Q, K_A P,
+    # bar_X bar_Q) 4.2 k, plant 0.1 k: 36 k
     out.append(loop_entry("tank_closed_loop", "BASELINE configs[2]: Tank_System.m l.170-291 with the Encoder_Tank lift "
                           "(nz = 10 + du augmentation, N = 20), 65 536 scenarios sharded over the ranks, T = 300, model "
-                          "from the package's joint Gram regression (l.93-100)", hi - lo, S_total, T, ms, 55.0e3, 6776,
+                          "from the package's joint Gram regression (l.93-100)", hi - lo, S_total, T, ms, 36.0e3, 6776,
                           loop.fused, int((loop.status != 0).sum().item()), "strong"))
     if rank == 0:
         jobs["tank_closed_loop"] = ("tank", At.cpu().numpy(), Bt.cpu().numpy(), Ct.cpu().numpy(), x0[0], 100, None)
@@ -379,7 +381,9 @@ def secondary_workloads(K, D, dev, rank, world, dmma_peak, hbm_peak, bf16_peak):
     ms = time_loop(loop, T, 1)
     out.append(loop_entry("rbf_horizon50_closed_loop", "BASELINE configs[4]: duffing_RBF.py (thin-plate RBF lift, 8 centres "
                           "of the reference run), horizon 50, warm-started update (l.434-438), 125 000 scenarios per GPU "
-                          "(1 M over 8), T = 100", S, S * world, T, ms, 2.8e6, 4536, loop.fused,
+                          "(1 M over 8), T = 100; flops: Krylov 50 x 2 x 64 + 50 x 36, H (Toeplitz sums, ny = 2) 5.1 k, ONE "
+                          "50 x 50 Cholesky + solves 47 k, 8 RBFs 0.3 k, RLS 2.6 k = 64 k with a direct solve (SURVEY.md 8d "
+                          "quotes 2.8 M for an iterative one)", S, S * world, T, ms, 64.0e3, 4536, loop.fused,
                           int((loop.status != 0).sum().item()), "weak"))
     if rank == 0:
         jobs["rbf_horizon50_closed_loop"] = ("rbf", Ar.cpu().numpy(), Br.cpu().numpy(), Cr.cpu().numpy(), x0[0], 30,

@@ -514,8 +514,10 @@ TcState* tc_state_create(const double* const* W, const double* const* b, const i
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (t->smem_bytes > max_smem) return fail();
-  if (cudaFuncSetAttribute(tc_encoder_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_bytes) != cudaSuccess ||
-      cudaFuncSetAttribute(tc_encoder_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_bytes) != cudaSuccess)
+  // the opt-in limit is a per-function attribute shared by every encoder handle of the process: raise it
+  // to the device maximum once (a per-handle value would be overwritten by the next, smaller net)
+  if (cudaFuncSetAttribute(tc_encoder_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(tc_encoder_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess)
     return fail();
   t->ok = true;
   return t;

@@ -70,12 +70,15 @@ def _two_loops(spec, x0, A, B, C, r, max_step, **kw):
     return out
 
 
-def _script(system, weights, max_step, x0, seed, save_dir, precision):
+def _script(system, weights, max_step, x0, seed, save_dir, precision, model=None):
     enc = weights if isinstance(weights, _lift.Encoder) else _lift.Encoder.from_file(weights)
-    np.random.seed(seed)                                   # duffing.py:47 / vanderpol.py:49
+    if seed is not None:
+        np.random.seed(seed)                               # duffing.py:47 (vanderpol.py:17 is commented out)
     gen = _dg.generate(100, 100)                           # duffing.py:72-76
     X, Y, U = gen.duffing_generate() if system == "duffing" else gen.vanderpol_generate()
     A, B, C, _ = identify(enc, X, Y, U, n_step=100, precision=precision)
+    if model is not None:                                  # replay a run from logged matrices
+        A, B, C = (torch.as_tensor(np.asarray(M, dtype=np.float64), device="cuda") for M in model)
     x0 = np.array([[-2.0, -2.0]]) if x0 is None else np.asarray(x0, dtype=np.float64).reshape(-1, 2)
     if system == "duffing":
         spec, r = _cl.duffing_spec(), np.array([1.0, 0.0])            # duffing.py:748-759
@@ -92,16 +95,19 @@ def _script(system, weights, max_step, x0, seed, save_dir, precision):
     return out
 
 
-def run_duffing(weights, max_step=300, x0=None, seed=101, save_dir=None, precision=_lift.PREC_FP64):
+def run_duffing(weights, max_step=300, x0=None, seed=101, save_dir=None, precision=_lift.PREC_FP64, model=None):
     """duffing.py end to end.  Returns the reference's arrays: A, B, C, logX / logU (frozen model),
     logXloc / logUloc (online update) as (S, n, T) / (S, T), Aloc, Bloc, Cloc, K_A, inv_K_G, bar_X,
     bar_Q after the last step."""
-    return _script("duffing", weights, max_step, x0, seed, save_dir, precision)
+    return _script("duffing", weights, max_step, x0, seed, save_dir, precision, model)
 
 
-def run_vanderpol(weights, max_step=400, x0=None, seed=50, save_dir=None, precision=_lift.PREC_FP64):
-    """vanderpol.py end to end (seed 50: vanderpol.py:49)."""
-    return _script("vanderpol", weights, max_step, x0, seed, save_dir, precision)
+def run_vanderpol(weights, max_step=400, x0=None, seed=None, save_dir=None, precision=_lift.PREC_FP64, model=None):
+    """vanderpol.py end to end.  The reference draws its EDMD snapshot set UNSEEDED (`np.random.seed(50)`
+    at vanderpol.py:17 is commented out; the first live seed, l.263, is for the open-loop test set), so
+    its A, B, C are not reproducible from a seed: `model=(A, B, C)` replays the closed loops from logged
+    matrices (tests/golden/ref_vanderpol.npz holds the reference run's)."""
+    return _script("vanderpol", weights, max_step, x0, seed, save_dir, precision, model)
 
 
 def run_rbf(cx, system="duffing", max_step=120, x0=None, seed=101, N=10):
@@ -123,6 +129,15 @@ def run_rbf(cx, system="duffing", max_step=120, x0=None, seed=101, N=10):
     p = pack.cpu().numpy()
     G, Aq, XV = p[:nv * nv].reshape(nv, nv), p[nv * nv:nv * nv + nz * nv].reshape(nz, nv), \
         p[nv * nv + nz * nv:nv * nv + (nz + 2) * nv].reshape(2, nv)
+    if system != "duffing":
+        # vanderpol_RBF.py:127-128 (a line shared with duffing_RBF.py) re-seeds and calls
+        # `duffing_generate()` again: from there on `X` is the DUFFING snapshot set (same inputs U: same
+        # draws), and the storage-method read-out C = X pinv(X_EX) (l.438) regresses those states on the
+        # VDP lifts.  Reproduced as is: the warm bar_X is X_duffing PHIX'.
+        np.random.seed(seed)
+        Xd, _, _ = _dg.generate(100, 100).duffing_generate()
+        pd = _edmd.gram_accumulate(PX, PY, U.reshape(-1), Xd.T.copy()).cpu().numpy()
+        XV = pd[nv * nv + nz * nv:nv * nv + (nz + 2) * nv].reshape(2, nv)
     x0 = np.array([[-2.0, -2.0]]) if x0 is None else np.asarray(x0, dtype=np.float64).reshape(-1, 2)
     S = x0.shape[0]
     pre, post = (_plant.DUFFING_PRE, _plant.DUFFING_POST) if system == "duffing" else (_plant.VDP_PRE, _plant.VDP_POST)

@@ -102,6 +102,24 @@ _np.savez(_OUT,
     RMSE=_np.asarray(RMSE), plotTime=plotTime)
 '''
 
+EPILOGUE_LOSS = r'''
+import numpy as _np
+import scipy.io as _sio
+def _n(v):
+    try:
+        return v.detach().numpy()
+    except AttributeError:
+        return _np.asarray(v)
+# training-loss evaluation of duffing.py:179-235 on the loaded weights (rec / multi-step lin / pred,
+# the reference's own accumulation order) + the Decoder half of the auto-encoder it needs
+_w = net.state_dict()
+_sio.savemat(_DEC, {"W%d" % (i + 1): _w["Decoder.%d.weight" % (2 * i)].numpy() for i in range(4)}
+             | {"b%d" % (i + 1): _w["Decoder.%d.bias" % (2 * i)].numpy() for i in range(4)})
+_np.savez(_OUT, Loss_rec=_n(Loss_rec), Loss_lin=_n(Loss_lin), Loss_pred=_n(Loss_pred), Loss=_n(Loss),
+          weight=_n(weight), A=_n(A), B=_n(B), pred_horizon=pred_horizon, batch=batch, batch_size=batch_size,
+          alphas=_np.array([alpha_1, alpha_2, alpha_3, alpha_4]), last_j=j)
+'''
+
 JOBS = {
     # name: (script, truncate-after-line (1-based, inclusive), steps, epilogue, needed files)
     "duffing": ("duffing.py", 1013, 300, EPILOGUE_ENC, ["AutoEncoder_20220418_duffing_2.pkl"]),
@@ -111,6 +129,8 @@ JOBS = {
     # open-loop multi-step predictor + its test snapshot set (no closed loop: steps = None)
     "duffing_predict": ("duffing.py", 343, None, EPILOGUE_PRED, ["AutoEncoder_20220418_duffing_2.pkl"]),
     "vanderpol_predict": ("vanderpol.py", 348, None, EPILOGUE_PRED, ["AutoEncoder_20220414_4.pkl"]),
+    # training-loss evaluation on the loaded weights (duffing.py:179-235), seed-101 snapshot set
+    "duffing_losses": ("duffing.py", 235, None, EPILOGUE_LOSS, ["AutoEncoder_20220418_duffing_2.pkl"]),
 }
 
 
@@ -129,7 +149,8 @@ def run_script(name):
             text, nsub = re.subn(r"^maxStep = 10000$", "maxStep = %d" % steps, text, flags=re.M)
             assert nsub == 1, "maxStep patch point not found"
         out = os.path.join(HERE, "ref_%s.npz" % name)
-        body = PROLOGUE + text + "\n_OUT = %r\n" % out + epilogue
+        dec = os.path.join(HERE, "weights", "duffing_decoder_weights.mat")
+        body = PROLOGUE + text + "\n_OUT = %r\n_DEC = %r\n" % (out, dec) + epilogue
         path = os.path.join(work, "run_" + script)
         with open(path, "w", encoding="utf-8") as fh:
             fh.write(body)

@@ -34,11 +34,24 @@ def test_script_end_to_end_matches_the_reference_run(system, tmp_path):
     against tests/golden/ref_<system>.npz (the reference script's own run in the build container)."""
     g = H.golden("ref_%s.npz" % system)
     T = int(g["maxStep"])
-    run = scripts.run_duffing if system == "duffing" else scripts.run_vanderpol
-    out = run(H.weights_path("duffing" if system == "duffing" else "vdp"), max_step=T, save_dir=str(tmp_path))
-    for k in ("A", "B", "C"):
-        assert _rel(out[k], g[k]) < 1e-9, (k, _rel(out[k], g[k]))
-    assert np.abs(out["X"][:, :300] - g["X_head"]).max() < 1e-12          # the reference's snapshot set
+    wsys = "duffing" if system == "duffing" else "vdp"
+    Ws, bs = H.oracle_weights(wsys)
+    if system == "duffing":
+        out = scripts.run_duffing(H.weights_path(wsys), max_step=T, save_dir=str(tmp_path))
+        for k in ("A", "B", "C"):
+            assert _rel(out[k], g[k]) < 1e-9, (k, _rel(out[k], g[k]))
+        assert np.abs(out["X"][:, :300] - g["X_head"]).max() < 1e-12      # the reference's snapshot set
+    else:
+        # vanderpol.py draws its EDMD snapshots unseeded (l.17 commented out): the package's own
+        # identification is checked against the oracle's pinv form on the same draws, the closed
+        # loops are replayed from the reference run's logged matrices
+        own = scripts.run_vanderpol(H.weights_path(wsys), max_step=5, seed=7)
+        from oracle import edmd as oedmd, lift as olift
+        Ao, Bo, Co = oedmd.edmd_pinv(olift.encoder_forward(Ws, bs, own["X"].T).T, olift.encoder_forward(Ws, bs, own["Y"].T).T,
+                                     own["U"], own["X"])
+        for k, want in (("A", Ao), ("B", Bo), ("C", Co)):
+            assert _rel(own[k], want) < 1e-9, (k, _rel(own[k], want))
+        out = scripts.run_vanderpol(H.weights_path(wsys), max_step=T, save_dir=str(tmp_path), model=(g["A"], g["B"], g["C"]))
     # update loop: the reference's own floor is 4e-5 (SURVEY.md section 4)
     assert np.abs(out["logXloc"][0] - g["logXloc"][:, :T]).max() < 2e-4
     # frozen loop: L-BFGS-B noise accumulates in the steady-state offset (1.3e-2 between scipy builds)
@@ -51,12 +64,12 @@ def test_script_end_to_end_matches_the_reference_run(system, tmp_path):
     import scipy.io as sio
     nn = sio.loadmat(str(tmp_path / "NN_Encoder.mat"))
     assert nn["X_Collection"].shape == (2, T) and nn["X_Collection_NO"].shape == (2, T) and nn["U_Collection"].shape == (1, T)
-    Ws, bs = K.weights.load_encoder_weights(str(tmp_path / "model_weights.mat"))
-    assert all(np.array_equal(a, b) for a, b in zip(Ws, H.oracle_weights("duffing" if system == "duffing" else "vdp")[0]))
-    # the same chain against the oracle from the PACKAGE's matrices (exact QP): tight
-    Ws, bs = H.oracle_weights("duffing" if system == "duffing" else "vdp")
+    W2, _ = K.weights.load_encoder_weights(str(tmp_path / "model_weights.mat"))
+    assert all(np.array_equal(a, b) for a, b in zip(W2, Ws))
+    # the same chain against the oracle from the matrices the loops used (exact QP): tight
     cfg = ocl.duffing_config(Ws, bs) if system == "duffing" else ocl.vanderpol_config(Ws, bs)
-    o = ocl.run_loop(cfg, out["A"], out["B"], out["C"], np.array([-2.0, -2.0]), 120, update=ocl.UPDATE_NONE, qp="exact")
+    Al, Bl, Cl = (out["A"], out["B"], out["C"]) if system == "duffing" else (g["A"], g["B"], g["C"])
+    o = ocl.run_loop(cfg, Al, Bl, Cl, np.array([-2.0, -2.0]), 120, update=ocl.UPDATE_NONE, qp="exact")
     assert np.abs(o["X"].T - out["logX"][0][:, :120]).max() < 1e-8
 
 
@@ -110,13 +123,24 @@ def test_koopman_update_m_closed_loop():
         assert not loop.fused                                   # nz = 10: generic kernels
         lx, lu = loop.log_x.cpu().numpy(), loop.log_u.cpu().numpy()
         cfg = replace(m["cfg"], lam=lam)
+        # lambda = 1 (the value in the file): the free-running loops agree to 1e-7 over all 100 steps.
+        # lambda < 1 winds the covariance up (P ~ lambda^-k in the unexcited directions): a 1e-16
+        # perturbation of P grows to 8e-8 by step 98 in the oracle itself, so the free-running bar is
+        # 1e-7 over the first 40 steps and 1e-3 overall, and every step is checked teacher-forced below
+        n_tight = T if lam == 1.0 else 40
         for s in range(len(x0)):
             w = orls.RLSState.warm(m["G"], m["Aq"], m["XV"][:, :nz], m["G"][:nz, :nz])
             o = ocl.run_loop(cfg, m["A"], m["B"], m["C"], x0[s], T, update=ocl.UPDATE_RLS, qp="exact", warm=w)
-            assert np.abs(o["X"] - lx[:, s]).max() < 1e-7, (lam, s)
-            assert np.abs(o["U"] - lu[:, s]).max() < 1e-6, (lam, s)
-            assert _rel(loop.A[s].cpu().numpy(), o["A"]) < 1e-6
+            assert np.abs(o["X"] - lx[:, s])[:n_tight].max() < 1e-7, (lam, s)
+            assert np.abs(o["U"] - lu[:, s])[:n_tight].max() < 1e-6, (lam, s)
+            assert np.abs(o["X"] - lx[:, s]).max() < 1e-3, (lam, s)
+            if lam == 1.0:
+                assert _rel(loop.A[s].cpu().numpy(), o["A"]) < 1e-6
         assert int(loop.status.max().item()) == 0
+        w = orls.RLSState.warm(m["G"], m["Aq"], m["XV"][:, :nz], m["G"][:nz, :nz])
+        got, want, _ = _teacher_forced(cfg, m["A"], m["B"], m["C"], x0[0], T, replace(spec, lam=lam), enc, cfg.r, warm=w)
+        assert np.abs(got["u"] - want["u"]).max() < 1e-7 and np.abs(got["x"] - want["x"]).max() < 1e-9
+        assert np.all(np.abs(got["A"] - want["A"]) <= 1e-6 * np.abs(want["A"]).reshape(len(want["A"]), -1).max(axis=1).reshape(-1, 1, 1))
         assert torch.equal(loop.C.cpu(), torch.from_numpy(np.broadcast_to(m["C"], (len(x0), 2, nz)).copy()))
     out = scripts.run_koopman_update(H.weights_path("duffing"), max_step=T, seed=m["seed"])
     for k in ("A", "B", "C"):
@@ -148,7 +172,14 @@ def test_tracking_lift_m_closed_loop():
             o = ocl.run_loop(m["cfg"], m["A"], m["B"], m["C"], x0[s], T, update=ocl.UPDATE_RLS, qp="exact")
             assert np.abs(o["X"] - lx[:, s]).max() <= xa, (name, s)
             assert np.abs(o["U"] - lu[:, s]).max() <= ua, (name, s)
-            assert np.abs(o["U"][late] - lu[late, s]).max() <= ul * max(1.0, np.abs(o["U"][late]).max()), (name, s)
+            # the plant switch at step 100 starts a second transient (the input oscillates while the RLS
+            # re-identifies): the late window of this loop gets the transient bar, single steps 1e-7 below
+            assert np.abs(o["U"][late] - lu[late, s]).max() <= ua, (name, s)
+    for x in x0[:2]:
+        got, want, _ = _teacher_forced(m["cfg"], m["A"], m["B"], m["C"], x, T, spec, enc, m["cfg"].r)
+        assert np.abs(got["u"] - want["u"]).max() < 1e-7 and np.abs(got["x"] - want["x"]).max() < 1e-9
+        assert np.abs(got["z"] - want["z_next"]).max() < 1e-9
+        assert np.all(np.abs(got["A"] - want["A"]) <= 1e-6 * np.maximum(np.abs(want["A"]).reshape(len(want["A"]), -1).max(axis=1), 1e-3).reshape(-1, 1, 1))
     out = scripts.run_tracking_lift(H.weights_path("vdp"), max_step=T, seed=m["seed"])
     for k in ("A", "B"):
         assert _rel(out[k], m[k]) < 1e-8, (k, _rel(out[k], m[k]))
@@ -156,10 +187,11 @@ def test_tracking_lift_m_closed_loop():
 
 
 # ------------------------------------------------------------------ teacher-forced single steps --
-def _teacher_forced(cfg, A, B, C, x0, T, spec, enc, r):
+def _teacher_forced(cfg, A, B, C, x0, T, spec, enc, r, warm=None):
     """Oracle trajectory with every pre-step state recorded -> ONE GPU batch of T - 1 single-step
     problems (steps 1 .. T - 1, the RLS already running) -> per-step comparison."""
-    o = ocl.run_loop(cfg, A, B, C, x0, T, update=ocl.UPDATE_RLS, qp="exact", record_states=True, record_models=True)
+    o = ocl.run_loop(cfg, A, B, C, x0, T, update=ocl.UPDATE_RLS, qp="exact", record_states=True, record_models=True,
+                     warm=warm)
     ps = o["pre_states"][1:]
     S = len(ps)
     nz = cfg.nz
@@ -229,7 +261,7 @@ def test_bench_batch_teacher_forced_over_the_full_horizon():
     rest = [int(s) for s in np.random.default_rng(1).permutation(S) if s not in set(pick)]
     pick = [int(s) for s in pick] + rest[:64 - len(pick)]
     assert len(pick) == 64
-    r_np = r.cpu().numpy()
+    r_np = np.asarray(r)
     n_blow = 0
     for s in pick:
         cfg = ocl.vanderpol_config(Ws, bs, xref[s])

@@ -161,6 +161,35 @@ def test_rbf_storage_method_is_warm_started_rls():
     np.testing.assert_allclose(rl["C"], lit["C"], atol=1e-9)
 
 
+def test_vanderpol_rbf_update_loop_regresses_C_on_the_duffing_states():
+    """vanderpol_RBF.py:127-128 re-seeds (101) and calls `duffing_generate()` again -- the line is
+    shared with duffing_RBF.py -- so from there on `X` holds the DUFFING snapshot states (and U the
+    same inputs: identical draws), and the storage-method read-out `C = X pinv(X_EX)` (l.438)
+    regresses duffing states on the VDP lifts.  With that quirk (warm bar_X = X_duffing PHIX') the
+    oracle reproduces the reference run's update loop to round-off; its frozen loop switches to the
+    duffing post-plant (l.328)."""
+    g = H.golden("ref_vanderpol_rbf.npz")
+    X, Y, U = plant.generate_snapshots(100, 100, plant.VDP_PRE, np.random.RandomState(101))
+    Xd, _, Ud = plant.generate_snapshots(100, 100, plant.DUFFING_PRE, np.random.RandomState(101))
+    assert np.array_equal(U, Ud)
+    PHIX, PHIY = lift.rbf_lift(X.T, g["cx"]).T, lift.rbf_lift(Y.T, g["cx"]).T
+    np.testing.assert_allclose(PHIX[:, :300], g["PHIX_head"], rtol=1e-10, atol=1e-12)
+    A, B, C = edmd.edmd_pinv(PHIX, PHIY, U, X)
+    np.testing.assert_allclose(A, g["A"], atol=1e-10)
+    np.testing.assert_allclose(C, g["C"], atol=1e-10)
+    cfg, T = ocl.rbf_config(g["cx"], "vanderpol"), int(g["maxStep"])
+    G, Aq, _ = edmd.gram_pack(PHIX, PHIY, U, X)
+    warm = rls.RLSState.warm(G, Aq, Xd @ PHIX.T, G[:8, :8])
+    o = ocl.run_loop(cfg, g["A"], g["B"], g["C"], [-2.0, -2.0], T, update=ocl.UPDATE_RLS, qp="exact", warm=warm)
+    assert np.abs(o["X"].T - g["logXloc"][:, :T]).max() < 1e-9      # saturated controls: exact agreement
+    assert np.abs(o["U"] - g["logUloc"][0, :T]).max() < 1e-9
+    np.testing.assert_allclose(np.linalg.norm(o["C"] - g["C"], 2) > 0.5, True)   # the read-out is indeed off
+    cfgf = ocl.rbf_config(g["cx"], "vanderpol")
+    cfgf.p_post = plant.DUFFING_POST
+    f = ocl.run_loop(cfgf, g["A"], g["B"], g["C"], [-2.0, -2.0], T, update=ocl.UPDATE_NONE, qp="exact")
+    assert np.abs(f["X"].T - g["logX"][:, :T]).max() < 2e-3
+
+
 def test_exact_qp_solver_against_bvls_and_lbfgsb():
     rs = np.random.RandomState(0)
     for _ in range(60):
