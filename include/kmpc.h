@@ -54,7 +54,10 @@ int64_t kmpc_launch_count(void);
 /* ------------------------------------------------------------------ stage 1: lifting ---------
  * theta_E encoder: duffing.py:21-29 (`net.Encoder`, call sites l.153,155,764,847,884),
  * vanderpol.py:154,672,679,760,769,805; Encoder_Duffing.m:3-6, Encoder_VDP.m:3-6, Encoder_Tank.m:3-5.
- * W[l] is HOST memory, nn.Linear layout (dims[l+1], dims[l]) row-major; b[l] HOST (dims[l+1]).   */
+ * W[l] is HOST memory, nn.Linear layout (dims[l+1], dims[l]) row-major; b[l] HOST (dims[l+1]).
+ * Input width dims[0] <= 16: the Decoder half (duffing.py:30-38, 8 -> 100 -> 100 -> 100 -> 2) is the
+ * same kind of handle (used by the training-loss evaluation); nets with dims[0] > 4 run on the
+ * CTA-wide fp64 tensor kernel and have no KMPC_PREC_TC path.                                      */
 typedef struct kmpc_encoder kmpc_encoder;
 
 #define KMPC_LIFT_RAW 0    /* theta(x)                        duffing.py:764                      */
@@ -266,8 +269,8 @@ int kmpc_generate_snapshots(const double* x0, const double* u0, const double* pa
 
 /* ------------------------------------------------------------------ open-loop predictor ------
  * duffing.py:290-343 / vanderpol.py:292-348: along T consecutive snapshots of each of n_seq
- * sequences (sequence s starts at snapshot s * seq_stride; the reference checks one: n_seq = 1,
- * T = plotTime) the lifted state restarts from the TRUE lifted state psi every reset_every (10)
+ * sequences (sequence s starts at snapshot s * seq_stride >= 1, windows may overlap; the reference
+ * checks one: n_seq = 1, T = plotTime) the lifted state restarts from the TRUE lifted state psi every reset_every (10)
  * steps and follows z+ = A z + B u in between; logged BEFORE the propagation: decoder_X (n_seq,T,nz)
  * = z and test_Y (n_seq,T,n) = C z.  psi [dev] (M, nz) = lift of the snapshots (kmpc_encode /
  * kmpc_rbf_lift), x [dev] (M, n), u [dev] (M).  rmse (nullable, [dev] (n_seq)):
@@ -276,6 +279,17 @@ int kmpc_open_loop_predict(const double* psi, const double* x, const double* u, 
                            const double* B, const double* C, int nz, int n, int64_t n_seq, int T,
                            int64_t seq_stride, int reset_every, int rmse_row, double* decoder_X,
                            double* test_Y, double* rmse, void* stream);
+
+/* ------------------------------------------------------------------ training-loss windows ----
+ * duffing.py:179-235 (and the loop body of DeepLearning_KoopmanControl_Approach3.py:462-563): for window
+ * w starting at snapshot k = k0 + w * stride, with zpred (W,T,nz) the linear rollout of the window
+ * (kmpc_open_loop_predict with seq_stride = stride, reset_every = T: zpred[w][0] = psi_k) and
+ * xdec (W,T,n) = Decoder(zpred) (a second kmpc_encoder holding the decoder half):
+ *   out[w] = { ||xdec[w][0] - x_k||^2,  sum_{p=1..T-1} ||zpred[w][p] - psi_{k+p}||^2,
+ *              sum_{p=1..T-1} ||x_{k+p} - xdec[w][p]||^2 }        (criterion = MSELoss(reduction='sum'))
+ * The reference's own accumulation over windows (l.179, 221-233) is host arithmetic on these sums.   */
+int kmpc_window_losses(const double* psi, const double* x, const double* zpred, const double* xdec, int nz,
+                       int n, int64_t W, int T, int64_t k0, int64_t stride, double* out, void* stream);
 
 /* ------------------------------------------------------------------ roofline denominators ----
  * MEASURED_PEAKS.json carries no fp64 number: measure this GPU's fp64 tensor-path

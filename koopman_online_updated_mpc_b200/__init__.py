@@ -13,10 +13,11 @@ the reference's call sites (duffing.py / vanderpol.py / duffing_RBF.py / Tank_Sy
     data_generate.generate(N, N_Traj)         snapshot generator (data_generate.py:12-152)
     predict.open_loop_predict(...)            open-loop model check (duffing.py:290-343)
     io_mat.save_model_weights / save_nn_encoder / save_trajectory   the reference's .mat layouts
+    losses.training_losses(enc, dec, X, U, A, B)  rec / multi-step lin / pred losses (duffing.py:179-235)
     scripts.run_duffing / run_vanderpol / run_rbf / run_tank / run_koopman_update / run_tracking_lift
                                               the reference's driver scripts, call sites swapped
 """
-from . import closed_loop, data_generate, distributed, edmd, io_mat, lift, mpc, plant, predict, rls, scripts, weights  # noqa: F401
+from . import closed_loop, data_generate, distributed, edmd, io_mat, lift, losses, mpc, plant, predict, rls, scripts, weights  # noqa: F401
 from ._lib import KmpcError, launch_count, lib, measure_fp64_peak  # noqa: F401
 from .build import build  # noqa: F401
 from .closed_loop import ClosedLoop, LoopSpec, duffing_spec, rbf_spec, tank_spec, vanderpol_spec  # noqa: F401

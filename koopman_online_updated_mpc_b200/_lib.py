@@ -60,6 +60,7 @@ _PROTOS = {
     "kmpc_measure_fp64_peak": (_i, [_c.POINTER(_d), _c.POINTER(_d), _vp]),
     "kmpc_generate_snapshots": (_i, [_vp, _vp, _vp, _i, _i, _d, _i64, _i, _vp, _vp, _vp, _vp]),
     "kmpc_open_loop_predict": (_i, [_vp] * 6 + [_i, _i, _i64, _i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
+    "kmpc_window_losses": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _i64, _i64, _vp, _vp]),
     "kmpc_closed_loop_steps_timed": (_i, [_vp, _i, _vp, _c.POINTER(_c.c_float)]),
 }
 

@@ -329,7 +329,7 @@ int kmpc_encoder_create(kmpc_encoder** out, const double* const* W, const double
   if (!out || !W || !b || !dims || n_layers < 1 || n_layers > KMPC_MAX_LAYERS) return KMPC_ERR_ARG;
   for (int l = 0; l <= n_layers; ++l)
     if (dims[l] < 1 || dims[l] > KMPC_MAX_WIDTH) return KMPC_ERR_ARG;
-  if (dims[0] > 4) return KMPC_ERR_ARG;
+  if (dims[0] > 16) return KMPC_ERR_ARG;
   cudaStream_t st = as_stream(stream);
   kmpc_encoder* enc = new kmpc_encoder();
   enc->p.n_layers = n_layers;
@@ -403,11 +403,11 @@ int kmpc_encoder_create(kmpc_encoder** out, const double* const* W, const double
   }
   // theta(0) for the OFFSET / STACK lift modes (Koopman_update.m:67)
   double* scratch = nullptr;
-  if (cudaMalloc(&scratch, (4 + KMPC_MAX_WIDTH) * sizeof(double)) != cudaSuccess) return fail(KMPC_ERR_ALLOC);
+  if (cudaMalloc(&scratch, (16 + KMPC_MAX_WIDTH) * sizeof(double)) != cudaSuccess) return fail(KMPC_ERR_ALLOC);
   enc->owned.push_back(scratch);
-  enc->d_z0 = scratch + 4;
+  enc->d_z0 = scratch + 16;
   enc->p.z0 = enc->d_z0;
-  if (cudaMemsetAsync(scratch, 0, (4 + KMPC_MAX_WIDTH) * sizeof(double), st) != cudaSuccess)
+  if (cudaMemsetAsync(scratch, 0, (16 + KMPC_MAX_WIDTH) * sizeof(double), st) != cudaSuccess)
     return fail(KMPC_ERR_CUDA);
   int rc = launch_encoder(enc, scratch, enc->d_z0, 1, KMPC_LIFT_RAW, st);
   if (rc != KMPC_OK) return fail(rc);

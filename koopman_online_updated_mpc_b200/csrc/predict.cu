@@ -129,11 +129,63 @@ __global__ void predict_rmse_kernel(const double* __restrict__ test_Y, const dou
   if (lane == 0) rmse[seq] = sqrt(acc);
 }
 
+// Training-loss window sums (duffing.py:179-235).  Window w starts at snapshot k = k0 + w * stride; one warp
+// per window, fixed summation order (lane-strided partials, xor-shuffle tree).  out[w] = {rec, lin, pred}:
+//   rec  = || Decoder(psi_k) - x_k ||^2                      (xdec[w][0])
+//   lin  = sum_{p=1..H} || zpred[w][p] - psi_{k+p} ||^2      (zpred = the linear rollout of the window)
+//   pred = sum_{p=1..H} || x_{k+p} - Decoder(zpred[w][p]) ||^2
+__global__ void window_losses_kernel(const double* __restrict__ psi, const double* __restrict__ x,
+                                     const double* __restrict__ zpred, const double* __restrict__ xdec, int nz,
+                                     int n, int64_t W, int T, int64_t k0, int64_t stride,
+                                     double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= W) return;
+  const int64_t k = k0 + w * stride;
+  double rec = 0.0, lin = 0.0, pred = 0.0;
+  for (int e = lane; e < n; e += 32) {
+    const double d = xdec[(w * T) * n + e] - x[k * n + e];
+    rec = fma(d, d, rec);
+  }
+  for (int e = lane; e < (T - 1) * nz; e += 32) {
+    const int p = 1 + e / nz, c = e - (p - 1) * nz;
+    const double d = zpred[(w * T + p) * nz + c] - psi[(k + p) * nz + c];
+    lin = fma(d, d, lin);
+  }
+  for (int e = lane; e < (T - 1) * n; e += 32) {
+    const int p = 1 + e / n, c = e - (p - 1) * n;
+    const double d = x[(k + p) * n + c] - xdec[(w * T + p) * n + c];
+    pred = fma(d, d, pred);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    rec += __shfl_xor_sync(0xffffffffu, rec, o);
+    lin += __shfl_xor_sync(0xffffffffu, lin, o);
+    pred += __shfl_xor_sync(0xffffffffu, pred, o);
+  }
+  if (lane == 0) {
+    out[w * 3 + 0] = rec;
+    out[w * 3 + 1] = lin;
+    out[w * 3 + 2] = pred;
+  }
+}
+
 }  // namespace kmpc
 
 using namespace kmpc;
 
 extern "C" {
+
+int kmpc_window_losses(const double* psi, const double* x, const double* zpred, const double* xdec, int nz, int n,
+                       int64_t W, int T, int64_t k0, int64_t stride, double* out, void* stream) {
+  if (nz < 1 || nz > KMPC_MAX_NZ || n < 1 || n > 4 || W < 0 || T < 1 || k0 < 0 || stride < 1) return KMPC_ERR_ARG;
+  if (W == 0) return KMPC_OK;
+  if (!psi || !x || !zpred || !xdec || !out) return KMPC_ERR_ARG;
+  const int64_t blocks = (W * 32 + 127) / 128;
+  if (blocks > 0x7fffffff) return KMPC_ERR_ARG;
+  window_losses_kernel<<<(unsigned)blocks, 128, 0, as_stream(stream)>>>(psi, x, zpred, xdec, nz, n, W, T, k0, stride, out);
+  KMPC_AFTER_LAUNCH();
+  return KMPC_OK;
+}
 
 int kmpc_generate_snapshots(const double* x0, const double* u0, const double* params, int plant_kind,
                             int rk4_variant, double h, int64_t n_traj, int n_step, double* X, double* Y,
@@ -155,7 +207,7 @@ int kmpc_open_loop_predict(const double* psi, const double* x, const double* u, 
                            int64_t seq_stride, int reset_every, int rmse_row, double* decoder_X,
                            double* test_Y, double* rmse, void* stream) {
   if (nz < 1 || nz > KMPC_MAX_NZ || n < 1 || n > 4 || n_seq < 0 || T < 0 || reset_every < 1) return KMPC_ERR_ARG;
-  if (seq_stride < T) return KMPC_ERR_ARG;
+  if (seq_stride < 1) return KMPC_ERR_ARG;   // windows may overlap (training-loss windows: stride 1)
   if (n_seq == 0 || T == 0) return KMPC_OK;
   if (!psi || !u || !A || !B || !C || !decoder_X || !test_Y) return KMPC_ERR_ARG;
   if (rmse && (!x || rmse_row < 0 || rmse_row >= n)) return KMPC_ERR_ARG;
