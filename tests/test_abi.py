@@ -69,7 +69,12 @@ def test_argument_validation_without_touching_the_gpu():
     assert L.kmpc_generate_snapshots(p, p, p, 7, 0, 0.05, 4, 10, p, p, p, None) == -1      # unknown plant
     assert L.kmpc_generate_snapshots(p, p, p, 0, 0, 0.05, 0, 10, p, p, p, None) == 0       # empty set
     assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 99, 2, 1, 10, 10, 10, 0, p, p, p, None) == -1   # nz out of range
-    assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 8, 2, 1, 10, 5, 10, 0, p, p, p, None) == -1    # stride < T
+    assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 8, 2, 1, 10, 0, 10, 0, p, p, p, None) == -1    # stride < 1
+    assert L.kmpc_window_losses(p, p, p, p, 99, 2, 4, 31, 0, 1, p, None) == -1                       # nz out of range
+    assert L.kmpc_window_losses(p, p, p, p, 8, 2, 4, 31, 0, 0, p, None) == -1                        # stride < 1
+    assert L.kmpc_window_losses(p, p, p, p, 8, 2, 0, 31, 0, 1, p, None) == 0                         # no windows
+    assert L.kmpc_encode_ex(None, p, p, 4, 0, 1, None) == -1
+    assert L.kmpc_gram_from_snapshots_ex(None, 0, 1, p, p, p, 4, p, None) == -1
     assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 8, 2, 1, 10, 10, 0, 0, p, p, p, None) == -1    # reset_every < 1
     assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 8, 2, 1, 10, 10, 10, 5, p, p, p, None) == -1   # rmse row out of range
     assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 8, 2, 0, 10, 10, 10, 0, p, p, p, None) == 0    # no sequences
