@@ -205,8 +205,10 @@ typedef struct kmpc_loop_config {
   double tol;
   int path;            /* KMPC_PATH_AUTO: persistent fused kernel when the shape allows it;
                           KMPC_PATH_GENERIC: always the per-step qp_plant -> lift -> rls kernels (cross-check) */
-  int qp_cold;         /* 1: generic kernels cold-start every QP like the reference (duffing.py:634: pastRes
-                          is never written back); 0: warm start from the previous step's moves (same minimiser) */
+  int qp_cold;         /* generic kernels: 0 = warm start from the previous step's moves, primal-dual sweeps then
+                          the primal method (same minimiser as a cold start); 1 = cold-start every QP like the
+                          reference (duffing.py:634: pastRes is never written back); 2 = warm start, primal
+                          method only (round-1 behaviour, kept for A/B timing) */
 } kmpc_loop_config;
 
 typedef struct kmpc_loop_buffers {     /* all [dev] */

@@ -46,7 +46,7 @@ class LoopSpec:
     q0: float = 100.0              # duffing.py:946
     tol: float = 0.0
     path: int = PATH_AUTO          # PATH_GENERIC: force the per-step generic kernels (cross-check of the fused one)
-    qp_cold: bool = False          # generic kernels: cold-start every QP (duffing.py:634) instead of warm starting
+    qp_cold: int = 0               # generic kernels: 0 warm start + sweeps, 1 cold start (duffing.py:634), 2 warm primal only
     params_pre: tuple = _plant.DUFFING_PRE
     params_post: tuple = _plant.DUFFING_POST
 

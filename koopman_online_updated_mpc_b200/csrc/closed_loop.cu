@@ -201,7 +201,7 @@ int kmpc_ctx_create(kmpc_ctx** out, const kmpc_loop_config* cfg, const kmpc_loop
   {
     // generic kernels: warm start from the previous step's optimal moves (0xFF bytes = NaN = none
     // yet).  cfg.qp_cold = 1 cold-starts every QP (explicit per-context option).
-    if (!ctx->fused && !c.qp_cold) {
+    if (!ctx->fused && c.qp_cold != 1) {
       if (cudaMalloc(&ctx->d.qp_x, (size_t)c.S * c.N * sizeof(double)) != cudaSuccess ||
           cudaMemsetAsync(ctx->d.qp_x, 0xFF, (size_t)c.S * c.N * sizeof(double), as_stream(stream)) != cudaSuccess) {
         kmpc_ctx_destroy(ctx);

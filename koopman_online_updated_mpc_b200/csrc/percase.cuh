@@ -633,7 +633,8 @@ constexpr int kPdasIters = 8;
 // set moves by a few bounds per step this costs a few factorisations, where a cold start needs
 // one per sweep and then one per bound of the final set whenever the sweeps cycle (Tank: 10 - 25).
 template <int G>
-KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol, bool warm = false) {
+KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol, bool warm = false,
+                           bool warm_sweeps = true) {
   int status = 0;
   int any = 0;
   double fmaxabs = 0.0;
@@ -677,7 +678,9 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol, bool
   if (warp_any(!done)) qp_gradient<G>(ws, N);  // grad at the start point; refreshed after each step
   for (int it = 0; it < max_iter; ++it) {
     if (!warp_any(!done)) break;
-    const bool pdas = !warm && it < kPdasIters;  // uniform over the warp
+    // primal-dual sweeps first, also from a warm working set (a good guess converges in 1 - 3 sweeps where
+    // the primal method needs one factorisation per changed bound); warm_sweeps = false: primal only
+    const bool pdas = (!warm || warm_sweeps) && it < kPdasIters;  // uniform over the warp
     KMPC_LANE_LOOP(i, N) ws.p[i] = (ws.W[i] == 0) ? -ws.grad[i] : 0.0;
     KMPC_SYNCWARP();
     const int cst = qp_chol_masked<G>(ws, N);

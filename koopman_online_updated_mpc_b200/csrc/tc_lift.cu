@@ -104,6 +104,20 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -244,50 +258,64 @@ tc_encoder_kernel(const __grid_constant__ CUtensorMap wmap, const TcDev p, const
     const uint32_t w_lo = umma_desc_lo(smem_u32(smem + L.w));   // descriptor of the first weight byte
     const uint32_t idesc_h = umma_idesc_bf16(kTcNP), idesc_o = umma_idesc_bf16(kTcNLast);
     const bool leader = elect_one();
-    uint32_t n_batch = 0, ready_cnt[2] = {0, 0};
-    for (int64_t it = 0; it < my_iters; ++it) {
-      for (int j = 0; j < n_batches; ++j) {
-        for (int slot = 0; slot < 2; ++slot) {
-          mbar_wait_bounded(&a_ready[slot], ready_cnt[slot] & 1);
-          ++ready_cnt[slot];
-          if (n_batch > 0) mbar_wait_bounded(acc_free, (n_batch - 1) & 1);
-          ++n_batch;
-          tc_fence_after();
-          if (leader) {
-            const uint32_t a_base = tmem_base + kTcACol0 + slot * kTcAColStride;
-            const uint32_t acc = tmem_base + kTcAccCol;
-            // order-2 products first, the dominant a0.b0 last (see the header); every descriptor is
-            // the layer's base plus a compile-time offset (16-byte units)
-            if (j < p.n_gemm) {
-              const uint32_t wl = w_lo + (uint32_t)j * (3 * kTcPieceBytes >> 4);
-#pragma unroll
-              for (int t = 0; t < 6; ++t) {
-                const int pa = (t == 0) ? 2 : ((t == 1 || t == 3) ? 1 : 0);
-                const int pb = (t == 2) ? 2 : ((t == 1 || t == 4) ? 1 : 0);
-#pragma unroll
-                for (int ks = 0; ks < kTcKS; ++ks)
-                  umma_ts(acc, a_base + pa * (kTcNP / 2) + ks * 8,
-                          wl + ((pb * kTcPieceBytes + (ks >> 2) * kTcBlkBytes + (ks & 3) * 32) >> 4), kDescHiSw128,
-                          idesc_h, (t | ks) ? 1u : 0u);
-              }
-            } else {
-              const uint32_t wl = w_lo + (uint32_t)p.n_gemm * (3 * kTcPieceBytes >> 4);
-#pragma unroll
-              for (int t = 0; t < 6; ++t) {
-                const int pa = (t == 0) ? 2 : ((t == 1 || t == 3) ? 1 : 0);
-                const int pb = (t == 2) ? 2 : ((t == 1 || t == 4) ? 1 : 0);
-#pragma unroll
-                for (int ks = 0; ks < kTcKS; ++ks)
-                  umma_ts(acc, a_base + pa * (kTcNP / 2) + ks * 8,
-                          wl + ((pb * kTcLastPieceBytes + (ks >> 2) * kTcLastBlkBytes + (ks & 3) * 32) >> 4),
-                          kDescHiSw128, idesc_o, (t | ks) ? 1u : 0u);
-              }
-            }
-            umma_commit(&acc_full[slot]);
-          }
-          __syncwarp();
+    // Batches are served in the order the slots become ready (not strictly alternating): the two
+    // warpgroups run half a period out of phase (warpgroup 1 starts its first tile when slot 0's first
+    // batch is issued), so that one slot's CUDA-core phases (layer 0, epilogues) overlap the other slot's
+    // tensor batches.  done[s] = batches issued for slot s; its layer is done[s] % n_batches.
+    const int64_t total = my_iters * n_batches;
+    int64_t done0 = 0, done1 = 0;   // scalars (a two-element array indexed by `slot` would live in local memory)
+    uint32_t n_batch = 0;
+    int slot = 0;
+    while (done0 < total || done1 < total) {
+      int64_t d = slot ? done1 : done0;
+      if (d >= total || !mbar_test(&a_ready[slot], (uint32_t)d & 1)) {
+        slot ^= 1;
+        d = slot ? done1 : done0;
+        if (d >= total || !mbar_test(&a_ready[slot], (uint32_t)d & 1)) {
+          __nanosleep(32);
+          continue;
         }
       }
+      const int j = (int)(d % n_batches);
+      if (slot) ++done1;
+      else ++done0;
+      if (n_batch > 0) mbar_wait_bounded(acc_free, (n_batch - 1) & 1);
+      ++n_batch;
+      tc_fence_after();
+      if (leader) {
+        const uint32_t a_base = tmem_base + kTcACol0 + slot * kTcAColStride;
+        const uint32_t acc = tmem_base + kTcAccCol;
+        // order-2 products first, the dominant a0.b0 last (see the header); every descriptor is
+        // the layer's base plus a compile-time offset (16-byte units)
+        if (j < p.n_gemm) {
+          const uint32_t wl = w_lo + (uint32_t)j * (3 * kTcPieceBytes >> 4);
+#pragma unroll
+          for (int t = 0; t < 6; ++t) {
+            const int pa = (t == 0) ? 2 : ((t == 1 || t == 3) ? 1 : 0);
+            const int pb = (t == 2) ? 2 : ((t == 1 || t == 4) ? 1 : 0);
+#pragma unroll
+            for (int ks = 0; ks < kTcKS; ++ks)
+              umma_ts(acc, a_base + pa * (kTcNP / 2) + ks * 8,
+                      wl + ((pb * kTcPieceBytes + (ks >> 2) * kTcBlkBytes + (ks & 3) * 32) >> 4), kDescHiSw128,
+                      idesc_h, (t | ks) ? 1u : 0u);
+          }
+        } else {
+          const uint32_t wl = w_lo + (uint32_t)p.n_gemm * (3 * kTcPieceBytes >> 4);
+#pragma unroll
+          for (int t = 0; t < 6; ++t) {
+            const int pa = (t == 0) ? 2 : ((t == 1 || t == 3) ? 1 : 0);
+            const int pb = (t == 2) ? 2 : ((t == 1 || t == 4) ? 1 : 0);
+#pragma unroll
+            for (int ks = 0; ks < kTcKS; ++ks)
+              umma_ts(acc, a_base + pa * (kTcNP / 2) + ks * 8,
+                      wl + ((pb * kTcLastPieceBytes + (ks >> 2) * kTcLastBlkBytes + (ks & 3) * 32) >> 4),
+                      kDescHiSw128, idesc_o, (t | ks) ? 1u : 0u);
+          }
+        }
+        umma_commit(&acc_full[slot]);
+      }
+      __syncwarp();
+      slot ^= 1;   // look at the other slot first next time
     }
   } else {
     // ================= epilogue warpgroups: slot = warpgroup =================
@@ -297,19 +325,28 @@ tc_encoder_kernel(const __grid_constant__ CUtensorMap wmap, const TcDev p, const
     const uint32_t acc_lane_base = lane_base + kTcAccCol;
     const int n = p.n_in, off = (lift_mode == KMPC_LIFT_STACK) ? n : 0;
     uint32_t full_cnt = 0;
+    // this thread's row of a tile: x is prefetched one tile ahead (the load is in flight during the
+    // whole previous tile instead of stalling layer 0)
+    auto load_x = [&](int64_t it, double (&xv)[4]) {
+      const int64_t r = (((int64_t)blockIdx.x + it * gridDim.x) * 2 + slot) * kTcRows + row_in;
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) xv[k] = (k < n && it < my_iters && r < S) ? __ldg(x + r * n + k) : 0.0;
+    };
+    double xnext[4] = {0.0, 0.0, 0.0, 0.0};
+    load_x(0, xnext);
+    // half-period stagger: warpgroup 1 starts once slot 0's first A operand is in TMEM
+    if (slot == 1 && my_iters > 0) mbar_wait_bounded(&a_ready[0], 0);
     for (int64_t it = 0; it < my_iters; ++it) {
       const int64_t tile = ((int64_t)blockIdx.x + it * gridDim.x) * 2 + slot;
       const int64_t row = tile * kTcRows + row_in;
       const bool valid = row < S;
       // ---- layer 0 on CUDA cores (fp64): h = relu(W1 x + b1) -> A pieces ----
-      double xin[4] = {0.0, 0.0, 0.0, 0.0};
-      if (valid) {
+      double xin[4] = {xnext[0], xnext[1], xnext[2], xnext[3]};
+      load_x(it + 1, xnext);
+      if (valid && lift_mode == KMPC_LIFT_STACK) {
 #pragma unroll
         for (int k = 0; k < NIN; ++k)
-          if (k < n) {
-            xin[k] = x[row * n + k];
-            if (lift_mode == KMPC_LIFT_STACK) z[row * out_dim + k] = xin[k];
-          }
+          if (k < n) z[row * out_dim + k] = xin[k];
       }
       // branch-free: the table is zero beyond d1 / n_in, so padded outputs come out as relu(0) = 0
 #pragma unroll 1
