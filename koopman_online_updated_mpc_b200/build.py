@@ -16,6 +16,12 @@ NVCC_FLAGS = ["-Xcompiler", "-fPIC", "-O3", "-lineinfo", "-std=c++17",
               "-gencode", "arch=compute_100a,code=sm_100a"]
 
 
+def _flags():
+    """NVCC_FLAGS plus developer extras from KMPC_NVCC_EXTRA (build time only, e.g. -DKMPC_PROFILING)."""
+    extra = os.environ.get("KMPC_NVCC_EXTRA", "").split()
+    return NVCC_FLAGS + extra
+
+
 def _headers():
     hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hs.append(os.path.join(PKG_DIR, "..", "include", "kmpc.h"))
@@ -47,7 +53,7 @@ def build(force=False, verbose=False):
         if (not force and os.path.exists(o)
                 and os.path.getmtime(o) > max(os.path.getmtime(s), hdr_time)):
             return o
-        cmd = [nvcc, "-c"] + NVCC_FLAGS + ["-o", o, s]
+        cmd = [nvcc, "-c"] + _flags() + ["-o", o, s]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

@@ -86,6 +86,7 @@ gram_kernel(const double* __restrict__ psi, const double* __restrict__ psin,
     const int r = e / NV, c = e - r * NV;
     atomicAdd(pack + e, red[c / CB][r * CB + (c % CB)]);
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(pack + NR * NV, (double)M);   // snapshot count (exact)
 }
 
 // Generic path (any nz <= KMPC_MAX_NZ): one thread per output element and block-strided
@@ -172,8 +173,12 @@ int gram_accumulate_impl(const double* psi, const double* psi_next, const double
   const unsigned grid = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
   if (nz == 8 && n == 2) {
     gram_kernel<8, 2><<<grid, 64 * 3, 0, st>>>(psi, psi_next, u, x, M, pack, seg);
+    KMPC_AFTER_LAUNCH();
+    return KMPC_OK;
   } else if (nz == 10 && n == 2) {
     gram_kernel<10, 2><<<grid, 64 * 4, 0, st>>>(psi, psi_next, u, x, M, pack, seg);
+    KMPC_AFTER_LAUNCH();
+    return KMPC_OK;
   } else {
     const int nv = nz + 1, outs = (nv + nz + n) * nv;
     const unsigned g2 = (unsigned)(M < (int64_t)sms * 4 ? M : (int64_t)sms * 4);

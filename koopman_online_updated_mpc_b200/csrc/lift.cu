@@ -461,7 +461,11 @@ int kmpc_encoder_has_tc(const kmpc_encoder* enc) { return (enc && enc->tc) ? 1 :
 
 // The lift workspace of a handle: sized from the actual widths, serialised across callers.
 namespace {
-constexpr int64_t kGramChunk = 1 << 18;   // 262144 rows: 2 x 16 MiB of lifted states at nz = 8 stay in L2
+// Rows lifted per chunk.  Round 1 used 2^18 (the lifted chunk stays in L2), but at the tcgen05 lift's
+// 3.4e9 rows/s a 10 M-snapshot regression then spent 40 % of its time in the 39 x 3 short launches and
+// their atomics tails (profiles/r2/launches_edmd_tc_chunk18.txt); 2^22 rows (256 MiB of lifted states,
+// one HBM round trip at 6.5 TB/s = 0.1 ms) leaves 3 chunks.
+constexpr int64_t kGramChunk = 1 << 22;
 struct WsLock {
   kmpc_encoder* enc;
   cudaStream_t st;

@@ -403,60 +403,106 @@ KMPC_DEV void qp_build_warp(const QpWs& ws, int nzq, int ny, int N, bool identit
 // The host emulator (tests/hostemu) runs the lane-loop versions below; results agree to rounding.
 constexpr int kQpSlotsMax = KMPC_MAX_HORIZON / 16;
 
+// Free-set compaction.  The working set of a Tank / horizon-50 QP in a transient holds most of the
+// variables (measured on the Tank loop: 7.9 free of 20 on average over all factorisations), so the
+// factorisation and the triangular solves run on the COMPACTED free block: compact row c <-> original
+// variable orig(c), increasing.  Every lane of the group knows the free mask (ballot), lane c owns
+// compact rows c, c + G, ... and carries their original indices; the column owner broadcasts its
+// original index by shuffle.  ws.L / ws.invd hold the compact factor (nf(nf+1)/2 entries).
+// Loop trip counts use the maximum nf over the groups of the warp (the shuffles are warp-wide).
+template <int G>
+struct QpFreeMap {
+  static constexpr int SLOTS = KMPC_MAX_HORIZON / G;
+  int nf, nfw;       // free variables of this group / maximum over the groups of the warp
+  int oi[SLOTS];     // original index of compact row lane + sl * G (-1 beyond nf)
+  __device__ __forceinline__ void build(const QpWs& ws, int N) {
+    const int lane = threadIdx.x & (G - 1);
+    unsigned bits[SLOTS];
+    int cum[SLOTS + 1];
+    cum[0] = 0;
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+      const int i = lane + sl * G;
+      const bool fr = (i < N) && (ws.W[i] == 0);
+      unsigned b = __ballot_sync(0xffffffffu, fr);
+      if (G < 32) b = (b >> (threadIdx.x & 31 & ~(G - 1))) & ((1u << G) - 1u);
+      bits[sl] = b;
+      cum[sl + 1] = cum[sl] + __popc(b);
+    }
+    nf = cum[SLOTS];
+    nfw = nf;
+    if (G < 32) {
+#pragma unroll
+      for (int o = G; o < 32; o <<= 1) nfw = max(nfw, __shfl_xor_sync(0xffffffffu, nfw, o));
+    }
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+      const int c = lane + sl * G;
+      int o = -1;
+#pragma unroll
+      for (int s2 = 0; s2 < SLOTS; ++s2)
+        if (c >= cum[s2] && c < cum[s2 + 1]) o = s2 * G + (int)__fns(bits[s2], 0, c - cum[s2] + 1);
+      oi[sl] = o;
+    }
+  }
+};
+
 template <int G>
 __device__ __forceinline__ int qp_chol_masked_rows(const QpWs& ws, int N) {
   constexpr int SLOTS = KMPC_MAX_HORIZON / G;
   const int lane = threadIdx.x & (G - 1);
   int status = 0;
-  bool mrow[SLOTS];
+  QpFreeMap<G> fm;
+  fm.build(ws, N);
+  const int nf = fm.nf;
 #pragma unroll
-  for (int sl = 0; sl < SLOTS; ++sl) {
-    const int i = lane + sl * G;
-    mrow[sl] = (i < N) ? (ws.W[i] != 0) : true;
-  }
-  for (int j = 0; j < N; ++j) {
-    const bool mj = ws.W[j] != 0;
-    const double* rowj = ws.L + tri(j, 0);
-    double sv[SLOTS], dmine = 0.0;
+  for (int so = 0; so < SLOTS; ++so) {
+    for (int j = so * G; j < fm.nfw && j < (so + 1) * G; ++j) {
+      const int oj = __shfl_sync(0xffffffffu, fm.oi[so], j & (G - 1), G);   // -1 when j >= nf (another group's column)
+      const bool live = j < nf;
+      const double* rowj = ws.L + tri(j, 0);
+      double sv[SLOTS], dmine = 1.0;
 #pragma unroll
-    for (int sl = 0; sl < SLOTS; ++sl) {
-      const int i = lane + sl * G;
-      double v = 0.0;
-      if (i >= j && i < N && !mj && !mrow[sl]) {
-        const double* rowi = ws.L + tri(i, 0);
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int k = 0;
-        for (; k + 3 < j; k += 4) {
-          s0 = fma(rowi[k], rowj[k], s0);
-          s1 = fma(rowi[k + 1], rowj[k + 1], s1);
-          s2 = fma(rowi[k + 2], rowj[k + 2], s2);
-          s3 = fma(rowi[k + 3], rowj[k + 3], s3);
+      for (int sl = 0; sl < SLOTS; ++sl) {
+        const int i = lane + sl * G;
+        double v = 0.0;
+        if (live && i >= j && i < nf) {
+          const double* rowi = ws.L + tri(i, 0);
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          int k = 0;
+          for (; k + 3 < j; k += 4) {
+            s0 = fma(rowi[k], rowj[k], s0);
+            s1 = fma(rowi[k + 1], rowj[k + 1], s1);
+            s2 = fma(rowi[k + 2], rowj[k + 2], s2);
+            s3 = fma(rowi[k + 3], rowj[k + 3], s3);
+          }
+          for (; k < j; ++k) s0 = fma(rowi[k], rowj[k], s0);
+          v = 2.0 * ws.H[tri(fm.oi[sl], oj)] - ((s0 + s1) + (s2 + s3));
+          if (i == j) dmine = v;
         }
-        for (; k < j; ++k) s0 = fma(rowi[k], rowj[k], s0);
-        v = 2.0 * ws.H[tri(i, j)] - ((s0 + s1) + (s2 + s3));
+        sv[sl] = v;
       }
-      sv[sl] = v;
-      if (i == j) dmine = v;
-    }
-    double d = __shfl_sync(0xffffffffu, dmine, j & (G - 1), G);
-    if (mj) d = 1.0;
-    const double floor_j = mj ? 0.0 : kPivotFloor * (2.0 * ws.H[tri(j, j)]);
-    if (!(d > floor_j)) {  // numerically semi-definite: regularise and flag (oracle/mpc.py PIVOT_FLOOR)
-      status |= KMPC_STATUS_PIVOT;
-      d = floor_j;
-    }
-    const double inv = rsqrt(d);
+      double d = __shfl_sync(0xffffffffu, dmine, j & (G - 1), G);
+      const double floor_j = live ? kPivotFloor * (2.0 * ws.H[tri(oj, oj)]) : 0.0;
+      if (live && !(d > floor_j)) {  // numerically semi-definite: regularise and flag (oracle/mpc.py PIVOT_FLOOR)
+        status |= KMPC_STATUS_PIVOT;
+        d = floor_j;
+      }
+      const double inv = rsqrt(d);
+      if (live) {
 #pragma unroll
-    for (int sl = 0; sl < SLOTS; ++sl) {
-      const int i = lane + sl * G;
-      if (i == j) {
-        ws.L[tri(j, j)] = d * inv;
-        ws.invd[j] = inv;
-      } else if (i > j && i < N) {
-        ws.L[tri(i, j)] = sv[sl] * inv;
+        for (int sl = 0; sl < SLOTS; ++sl) {
+          const int i = lane + sl * G;
+          if (i == j) {
+            ws.L[tri(j, j)] = d * inv;
+            ws.invd[j] = inv;
+          } else if (i > j && i < nf) {
+            ws.L[tri(i, j)] = sv[sl] * inv;
+          }
+        }
       }
+      __syncwarp();
     }
-    __syncwarp();
   }
   return status;
 }
@@ -465,40 +511,49 @@ template <int G>
 __device__ __forceinline__ void qp_chol_solve_rows(const QpWs& ws, int N) {
   constexpr int SLOTS = KMPC_MAX_HORIZON / G;
   const int lane = threadIdx.x & (G - 1);
+  QpFreeMap<G> fm;
+  fm.build(ws, N);
+  const int nf = fm.nf;
   double pr[SLOTS];
 #pragma unroll
-  for (int sl = 0; sl < SLOTS; ++sl) pr[sl] = (lane + sl * G < N) ? ws.p[lane + sl * G] : 0.0;
+  for (int sl = 0; sl < SLOTS; ++sl) pr[sl] = (lane + sl * G < nf) ? ws.p[fm.oi[sl]] : 0.0;
   // forward: y_j = p_j / L_jj, then p_i -= L_ij y_j for the rows below
 #pragma unroll
   for (int so = 0; so < SLOTS; ++so) {
-    for (int j = so * G; j < N && j < (so + 1) * G; ++j) {
-      const double yj = __shfl_sync(0xffffffffu, pr[so], j & (G - 1), G) * ws.invd[j];
+    for (int j = so * G; j < fm.nfw && j < (so + 1) * G; ++j) {
+      const bool live = j < nf;
+      const double yj = __shfl_sync(0xffffffffu, pr[so], j & (G - 1), G) * (live ? ws.invd[j] : 0.0);
+      if (live) {
 #pragma unroll
-      for (int sl = 0; sl < SLOTS; ++sl) {
-        const int i = lane + sl * G;
-        if (i > j && i < N) pr[sl] = fma(-ws.L[tri(i, j)], yj, pr[sl]);
+        for (int sl = 0; sl < SLOTS; ++sl) {
+          const int i = lane + sl * G;
+          if (i > j && i < nf) pr[sl] = fma(-ws.L[tri(i, j)], yj, pr[sl]);
+        }
+        if (lane == (j & (G - 1))) pr[so] = yj;
       }
-      if (lane == (j & (G - 1))) pr[so] = yj;
     }
   }
   // backward: x_j = y_j / L_jj, then y_i -= L_ji x_j for the rows above (row j of L: coalesced)
 #pragma unroll
   for (int so = SLOTS - 1; so >= 0; --so) {
-    const int jhi = (N < (so + 1) * G ? N : (so + 1) * G) - 1;
+    const int jhi = (fm.nfw < (so + 1) * G ? fm.nfw : (so + 1) * G) - 1;
     for (int j = jhi; j >= so * G; --j) {
-      const double xj = __shfl_sync(0xffffffffu, pr[so], j & (G - 1), G) * ws.invd[j];
-      const double* rowj = ws.L + tri(j, 0);
+      const bool live = j < nf;
+      const double xj = __shfl_sync(0xffffffffu, pr[so], j & (G - 1), G) * (live ? ws.invd[j] : 0.0);
+      if (live) {
+        const double* rowj = ws.L + tri(j, 0);
 #pragma unroll
-      for (int sl = 0; sl < SLOTS; ++sl) {
-        const int i = lane + sl * G;
-        if (i < j) pr[sl] = fma(-rowj[i], xj, pr[sl]);
+        for (int sl = 0; sl < SLOTS; ++sl) {
+          const int i = lane + sl * G;
+          if (i < j) pr[sl] = fma(-rowj[i], xj, pr[sl]);
+        }
+        if (lane == (j & (G - 1))) pr[so] = xj;
       }
-      if (lane == (j & (G - 1))) pr[so] = xj;
     }
   }
 #pragma unroll
   for (int sl = 0; sl < SLOTS; ++sl)
-    if (lane + sl * G < N) ws.p[lane + sl * G] = pr[sl];
+    if (lane + sl * G < nf) ws.p[fm.oi[sl]] = pr[sl];
   __syncwarp();
 }
 

