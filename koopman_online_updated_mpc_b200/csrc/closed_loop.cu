@@ -96,14 +96,13 @@ static bool select_launch(const kmpc_loop_config& c, LoopLaunch* L) {
   const int rls_ws = rls_ws_doubles(c.nz, 2) * (int)sizeof(double);
   L->qp_spb = kLoopThreads / L->qp_g;
   while (L->qp_spb > 1 && L->qp_spb * qp_ws > budget) L->qp_spb >>= 1;
-  // a workspace so large that two default blocks do not fit an SM (N = 50: 32 KB per scenario): one
-  // block with as many scenarios as the SM's shared memory holds instead (7 warps instead of 4)
+  // One scenario per block for the warp-per-scenario shapes (Tank, horizon 50): the active-set iteration
+  // count of a scenario-step is heavy-tailed (Tank: 0 .. 50 factorisations, 25 % of the steps do 86 % of
+  // them), and a block retires only when its slowest scenario is done -- ncu measured 10.4 active warps
+  // per SM of 20 resident with 4 scenarios per block.  Single-warp blocks retire independently, and the
+  // SM holds as many as its shared memory allows (Tank: 23, horizon 50: 7).
+  if (L->qp_g == 32) L->qp_spb = 1;
   const int sm_smem = 225 * 1024;
-  if (2 * (L->qp_spb * qp_ws + 1024) > sm_smem) {
-    int spb = sm_smem / qp_ws;
-    if (spb > kLoopThreadsMax / L->qp_g) spb = kLoopThreadsMax / L->qp_g;
-    if (spb > L->qp_spb) L->qp_spb = spb;
-  }
   L->rls_spb = kLoopThreads / L->rls_g;
   while (L->rls_spb > 1 && L->rls_spb * rls_ws > budget) L->rls_spb >>= 1;
   L->qp_smem = L->qp_spb * qp_ws;
