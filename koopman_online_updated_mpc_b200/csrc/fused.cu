@@ -43,6 +43,7 @@ constexpr int FN = 10;           // horizon
 constexpr int FNV = FNZ + 1;
 constexpr int kScr = 184;        // scratch doubles per scenario (== 8 mod 16: the two scenarios of a
                                  // half-warp land on disjoint banks)
+constexpr unsigned kSetMask = (1u << FN) - 1u, kKeepBit = 1u << 31;   // wset word 0: working set | warm-start policy
 constexpr int kRedPitch = 9;     // pitch of the 8 x 8 reduction buffer (conflict-free column reads)
 // scratch layout during the QP build and the RLS
 constexpr int oRED = 0;          // [8][kRedPitch] cross-lane reduction buffer
@@ -128,11 +129,9 @@ __device__ __forceinline__ void group_gather(double* ex, int l, double mine, dou
 // with its state frozen).  Same algorithm as percase.cuh qp_solve_warp / oracle
 // solve_box_qp_exact (primal-dual active-set sweeps, then the monotone primal method), started
 // from a warm working set.
-//   factor_solve: right-looking Cholesky of the free block of 2H.  Lane i owns row i, lanes 0..2
-//   also own rows 8, 9 and the right-hand side (row 10), so the forward substitution comes for
-//   free; every lane keeps a replicated copy of the running diagonal, hence of the pivots: ONE
-//   __syncwarp per column (the column is the exchange buffer).  The back substitution is done
-//   redundantly by every lane, which leaves the step p replicated in registers.
+//   factor_solve: Cholesky of the free block of 2H with the right-hand side carried along, done by
+//   every lane redundantly in registers (no exchange, no synchronisation), which leaves the step p
+//   replicated in registers.
 struct QpCoop {
   const double* HF;   // packed lower 2H (55) | f (10)
   double* sc;         // Lc (60) | xs (10) | gs (10)
@@ -141,69 +140,73 @@ struct QpCoop {
   int iters;          // active-set iterations of the last run()
   unsigned wlo, whi;  // working set: bit i set = variable i at its lower / upper bound
 
-  // p <- (2H)_FF^-1 rhs_F (0 on masked variables), rhs = -g on free variables; replicated result
+  // p <- (2H)_FF^-1 rhs_F (0 on masked variables), rhs = -g on free variables; replicated result.
+  // Every lane factors the whole (masked) 10 x 10 block in its own registers, left-looking: no
+  // exchange and no synchronisation inside the factorisation, and the 9 - j row chains of a column are
+  // independent (the cooperative right-looking form needed one shared-memory round trip per column;
+  // the redundant lanes cost nothing in a SIMT warp).  The sequence of roundings per entry is the one
+  // of the right-looking form: s = H_rj, then s = fma(-L_rk, L_jk, s) for k = 0 .. j-1, then s * inv_j.
+  template <int J>
+  __device__ __forceinline__ void factor_column(unsigned masked, const double* gs, double* Lc,
+                                                double (&L)[(FN * (FN - 1)) / 2], double (&invd)[FN],
+                                                double (&p)[FN], int& st) {
+    constexpr int bj = (J * (J - 1)) / 2;
+    const bool mj = (masked >> J) & 1u;
+    const double hjj = HF[(J * (J + 1)) / 2 + J];
+    double d = mj ? 1.0 : hjj;
+    double y = mj ? 0.0 : -gs[J];
+#pragma unroll
+    for (int k = 0; k < J; ++k) {
+      d = fma(-L[bj + k], L[bj + k], d);
+      y = fma(-p[k], L[bj + k], y);
+    }
+    const double floor_j = mj ? 0.0 : kPivotFloor * hjj;
+    if (!(d > floor_j)) {  // numerically semi-definite: regularise and flag (oracle/mpc.py PIVOT_FLOOR)
+      st |= KMPC_STATUS_PIVOT;
+      d = floor_j;
+    }
+    const double inv = rsqrt(d);
+    invd[J] = inv;
+    p[J] = y * inv;   // y_J (forward substitution rides along)
+#pragma unroll
+    for (int r = J + 1; r < FN; ++r) {
+      const int br = (r * (r - 1)) / 2;
+      double s = (mj || ((masked >> r) & 1u)) ? 0.0 : HF[(r * (r + 1)) / 2 + J];
+#pragma unroll
+      for (int k = 0; k < J; ++k) s = fma(-L[br + k], L[bj + k], s);
+      const double lrj = s * inv;
+      L[br + J] = lrj;
+      if (l == 0) Lc[br + J] = lrj;   // parked for the back substitution: row r leaves the registers after column r
+    }
+  }
+
   __device__ __forceinline__ int factor_solve(unsigned masked, double (&p)[FN]) {
-    double* Lc = sc;
+    static_assert(FN == 10, "factor_solve instantiates the ten columns by hand");
     const double* gs = sc + oGS;
-    const int r0 = l, r1 = l + 8;            // rows of this lane (r1 valid for l < 3; r1 == 10: rhs)
-    const bool has1 = l < 3;
-    const bool m0 = (masked >> r0) & 1u, m1 = (r1 < FN) && ((masked >> r1) & 1u);
-    const int b0 = (r0 * (r0 + 1)) >> 1, b1 = (r1 < FN) ? (r1 * (r1 + 1)) >> 1 : 0;
-    double a0[FNZ], a1[FN], dg[FN], invd[FN];
+    double* Lc = sc;
+    double L[(FN * (FN - 1)) / 2], invd[FN];   // strictly lower triangle, row r at r (r - 1) / 2
     int st = 0;
-    // all loads first (unconditional, clamped indices), the masks are applied with selects
-#pragma unroll
-    for (int k = 0; k < FN; ++k) {
-      if (k < FNZ) a0[k] = HF[b0 + min(k, r0)];
-      a1[k] = (l == 2) ? -gs[k] : HF[b1 + min(k, r1)];   // l == 2: the right-hand side row
-      dg[k] = HF[tri(k, k)];
-    }
-#pragma unroll
-    for (int k = 0; k < FN; ++k) {
-      const bool mk = (masked >> k) & 1u;
-      if (k < FNZ) a0[k] = (m0 || mk || k > r0) ? 0.0 : a0[k];
-      a1[k] = (!has1 || mk || m1 || (r1 < FN && k > r1)) ? 0.0 : a1[k];
-      dg[k] = mk ? 1.0 : dg[k];
-    }
-#pragma unroll
-    for (int j = 0; j < FN; ++j) {
-      double d = dg[j];
-      const double floor_j = ((masked >> j) & 1u) ? 0.0 : kPivotFloor * HF[tri(j, j)];
-      if (!(d > floor_j)) {  // numerically semi-definite: regularise and flag (oracle/mpc.py PIVOT_FLOOR)
-        st |= KMPC_STATUS_PIVOT;
-        d = floor_j;
-      }
-      const double inv = rsqrt(d);
-      invd[j] = inv;
-      // column j: L[r][j] = a[r][j] / L[j][j] for the rows below the diagonal (and y_j in row 10)
-      double c0 = 0.0;
-      if (j < FNZ - 1) {
-        c0 = a0[j] * inv;
-        if (r0 > j) Lc[lcol(j) + r0 - j - 1] = c0;
-      }
-      const double c1 = a1[j] * inv;
-      if (has1 && r1 > j) Lc[lcol(j) + r1 - j - 1] = c1;
-      __syncwarp();
-      double col[FN + 1];
-#pragma unroll
-      for (int k = j + 1; k <= FN; ++k) col[k] = Lc[lcol(j) + k - j - 1];
-#pragma unroll
-      for (int k = j + 1; k < FN; ++k) {
-        if (k < FNZ) a0[k] = fma(-c0, col[k], a0[k]);
-        a1[k] = fma(-c1, col[k], a1[k]);
-        dg[k] = fma(-col[k], col[k], dg[k]);
-      }
-      p[j] = col[FN];   // y_j
-    }
-    // back substitution L' x = y, every lane redundantly
+    factor_column<0>(masked, gs, Lc, L, invd, p, st);
+    factor_column<1>(masked, gs, Lc, L, invd, p, st);
+    factor_column<2>(masked, gs, Lc, L, invd, p, st);
+    factor_column<3>(masked, gs, Lc, L, invd, p, st);
+    factor_column<4>(masked, gs, Lc, L, invd, p, st);
+    factor_column<5>(masked, gs, Lc, L, invd, p, st);
+    factor_column<6>(masked, gs, Lc, L, invd, p, st);
+    factor_column<7>(masked, gs, Lc, L, invd, p, st);
+    factor_column<8>(masked, gs, Lc, L, invd, p, st);
+    factor_column<9>(masked, gs, Lc, L, invd, p, st);
+    __syncwarp();
+    // back substitution L' x = y
 #pragma unroll
     for (int jj = 0; jj < FN; ++jj) {
       const int j = FN - 1 - jj;
       double s0 = p[j], s1 = 0.0;
 #pragma unroll
       for (int r = j + 1; r < FN; ++r) {
-        if ((r - j) & 1) s0 = fma(-Lc[lcol(j) + r - j - 1], p[r], s0);
-        else s1 = fma(-Lc[lcol(j) + r - j - 1], p[r], s1);
+        const double lrj = Lc[((r * (r - 1)) >> 1) + j];
+        if ((r - j) & 1) s0 = fma(-lrj, p[r], s0);
+        else s1 = fma(-lrj, p[r], s1);
       }
       p[j] = (s0 + s1) * invd[j];
     }
@@ -659,12 +662,21 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
         qp.HF = HF;
         qp.sc = scr + oL;
         qp.l = l;
-        // warm start: last step's optimal working set, shifted by one move (receding horizon)
-        qp.wlo = (wlo >> 1) | (wlo & (1u << (FN - 1)));
-        qp.whi = (whi >> 1) | (whi & (1u << (FN - 1)));
+        // warm start: last step's optimal working set, either shifted by one move (receding horizon:
+        // right when the plan is being followed) or as it is (right when the pattern is stationary in
+        // the horizon frame, e.g. "first move free, the rest saturated" while the restarted model is
+        // still poor: the shifted guess then costs 2-4 sweeps EVERY step).  The guess that matched the
+        // optimum of the last step is used for the next one (kKeepBit of wlo, carried in wset).
+        const unsigned plo = wlo & kSetMask, phi = whi & kSetMask;
+        const unsigned slo = (plo >> 1) | (plo & (1u << (FN - 1))), shi = (phi >> 1) | (phi & (1u << (FN - 1)));
+        const bool keep = (wlo & kKeepBit) != 0u;
+        qp.wlo = keep ? plo : slo;
+        qp.whi = keep ? phi : shi;
         unew = qp.run(c.lb, c.ub, c.max_iter, c.tol);
         status |= qp.status;
-        wlo = qp.wlo;
+        const bool as_kept = qp.wlo == plo && qp.whi == phi, as_shifted = qp.wlo == slo && qp.whi == shi;
+        const bool keep_next = (as_kept != as_shifted) ? as_kept : keep;
+        wlo = qp.wlo | (keep_next ? kKeepBit : 0u);
         whi = qp.whi;
         if (l == 0) {
           const double* pp = (step < c.first_post_step ? b.params_pre : b.params_post) + s * 5;
