@@ -132,6 +132,18 @@ __device__ __forceinline__ void group_gather(double* ex, int l, double mine, dou
 //   factor_solve: Cholesky of the free block of 2H with the right-hand side carried along, done by
 //   every lane redundantly in registers (no exchange, no synchronisation), which leaves the step p
 //   replicated in registers.
+// 1 / sqrt(d) for a positive normal d (the pivots are floored above zero; NaN propagates): hardware
+// seed (MUFU.RSQ64H, ~2^-26 relative) and one third-order correction y (1 + e/2 + 3 e^2/8), e = 1 - d y^2,
+// which leaves ~2^-78 before the final rounding -- the accuracy of rsqrt() without its special-case paths.
+__device__ __forceinline__ double rsqrt_pos(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double t = d * y;
+  const double e = fma(-t, y, 1.0);
+  const double c = fma(0.375, e, 0.5);
+  return fma(y, e * c, y);
+}
+
 struct QpCoop {
   const double* HF;   // packed lower 2H (55) | f (10)
   double* sc;         // Lc (60) | xs (10) | gs (10)
@@ -146,12 +158,12 @@ struct QpCoop {
   // independent (the cooperative right-looking form needed one shared-memory round trip per column;
   // the redundant lanes cost nothing in a SIMT warp).  The sequence of roundings per entry is the one
   // of the right-looking form: s = H_rj, then s = fma(-L_rk, L_jk, s) for k = 0 .. j-1, then s * inv_j.
-  template <int J>
+  template <bool MASKED, int J>
   __device__ __forceinline__ void factor_column(unsigned masked, const double* gs, double* Lc,
                                                 double (&L)[(FN * (FN - 1)) / 2], double (&invd)[FN],
                                                 double (&p)[FN], int& st) {
     constexpr int bj = (J * (J - 1)) / 2;
-    const bool mj = (masked >> J) & 1u;
+    const bool mj = MASKED && ((masked >> J) & 1u);
     const double hjj = HF[(J * (J + 1)) / 2 + J];
     double d = mj ? 1.0 : hjj;
     double y = mj ? 0.0 : -gs[J];
@@ -165,13 +177,13 @@ struct QpCoop {
       st |= KMPC_STATUS_PIVOT;
       d = floor_j;
     }
-    const double inv = rsqrt(d);
+    const double inv = rsqrt_pos(d);
     invd[J] = inv;
     p[J] = y * inv;   // y_J (forward substitution rides along)
 #pragma unroll
     for (int r = J + 1; r < FN; ++r) {
       const int br = (r * (r - 1)) / 2;
-      double s = (mj || ((masked >> r) & 1u)) ? 0.0 : HF[(r * (r + 1)) / 2 + J];
+      double s = (mj || (MASKED && ((masked >> r) & 1u))) ? 0.0 : HF[(r * (r + 1)) / 2 + J];
 #pragma unroll
       for (int k = 0; k < J; ++k) s = fma(-L[br + k], L[bj + k], s);
       const double lrj = s * inv;
@@ -180,22 +192,24 @@ struct QpCoop {
     }
   }
 
+  // MASKED = false: empty working set (no selects at all), right-hand side -f straight from HF
+  template <bool MASKED>
   __device__ __forceinline__ int factor_solve(unsigned masked, double (&p)[FN]) {
     static_assert(FN == 10, "factor_solve instantiates the ten columns by hand");
-    const double* gs = sc + oGS;
+    const double* gs = MASKED ? sc + oGS : HF + 55;
     double* Lc = sc;
     double L[(FN * (FN - 1)) / 2], invd[FN];   // strictly lower triangle, row r at r (r - 1) / 2
     int st = 0;
-    factor_column<0>(masked, gs, Lc, L, invd, p, st);
-    factor_column<1>(masked, gs, Lc, L, invd, p, st);
-    factor_column<2>(masked, gs, Lc, L, invd, p, st);
-    factor_column<3>(masked, gs, Lc, L, invd, p, st);
-    factor_column<4>(masked, gs, Lc, L, invd, p, st);
-    factor_column<5>(masked, gs, Lc, L, invd, p, st);
-    factor_column<6>(masked, gs, Lc, L, invd, p, st);
-    factor_column<7>(masked, gs, Lc, L, invd, p, st);
-    factor_column<8>(masked, gs, Lc, L, invd, p, st);
-    factor_column<9>(masked, gs, Lc, L, invd, p, st);
+    factor_column<MASKED, 0>(masked, gs, Lc, L, invd, p, st);
+    factor_column<MASKED, 1>(masked, gs, Lc, L, invd, p, st);
+    factor_column<MASKED, 2>(masked, gs, Lc, L, invd, p, st);
+    factor_column<MASKED, 3>(masked, gs, Lc, L, invd, p, st);
+    factor_column<MASKED, 4>(masked, gs, Lc, L, invd, p, st);
+    factor_column<MASKED, 5>(masked, gs, Lc, L, invd, p, st);
+    factor_column<MASKED, 6>(masked, gs, Lc, L, invd, p, st);
+    factor_column<MASKED, 7>(masked, gs, Lc, L, invd, p, st);
+    factor_column<MASKED, 8>(masked, gs, Lc, L, invd, p, st);
+    factor_column<MASKED, 9>(masked, gs, Lc, L, invd, p, st);
     __syncwarp();
     // back substitution L' x = y
 #pragma unroll
@@ -268,7 +282,7 @@ struct QpCoop {
       const bool pdas = it < kPdasIters;
       const unsigned masked = wlo | whi;
       double p[FN];
-      const int st = factor_solve(masked, p);
+      const int st = factor_solve<true>(masked, p);
       if (!done) status |= st;
       double alpha = 1.0;
       int block = -1;
@@ -778,11 +792,17 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
         if (l == 0) Pm[80] = P88;
         __syncwarp();
 #pragma unroll 1
-        for (int j = 0; j < FNV; ++j) {   // column j of [A B]; j == 8 is B (HF[64 + l])
-          double sacc = 0.0;
+        for (int j = 0; j < FNV; j += 3) {   // columns j .. j + 2 of [A B] (three chains in flight); column 8 is B (HF[64 + l])
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
-          for (int k = 0; k < FNV; ++k) sacc = fma(KAr[k], Pm[k * 9 + j], sacc);
-          HF[j * 8 + l] = sacc;
+          for (int k = 0; k < FNV; ++k) {
+            s0 = fma(KAr[k], Pm[k * 9 + j], s0);
+            s1 = fma(KAr[k], Pm[k * 9 + j + 1], s1);
+            s2 = fma(KAr[k], Pm[k * 9 + j + 2], s2);
+          }
+          HF[j * 8 + l] = s0;
+          HF[(j + 1) * 8 + l] = s1;
+          HF[(j + 2) * 8 + l] = s2;
         }
         __syncwarp();
         if (upc) {
@@ -807,12 +827,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) fused_loop_kernel(const __grid
             Xc0 = fma(xc0, zl, Xc0);
             Xc1 = fma(xc1, zl, Xc1);
           }
+          // C = bar_X bar_Q: the QP reads it every step only with y = C z; with y = z it is an output of
+          // the launch and is formed once, from the final bar_X and bar_Q (same arithmetic)
+          if (OUT == KMPC_OUT_C || t == a.T - 1) {
 #pragma unroll
-          for (int j = 0; j < FNZ; ++j) ch[j] = Xc0 * Qr[j];
-          Cc0 = chunk_reduce(red, l, ch);
+            for (int j = 0; j < FNZ; ++j) ch[j] = Xc0 * Qr[j];
+            Cc0 = chunk_reduce(red, l, ch);
 #pragma unroll
-          for (int j = 0; j < FNZ; ++j) ch[j] = Xc1 * Qr[j];
-          Cc1 = chunk_reduce(red, l, ch);
+            for (int j = 0; j < FNZ; ++j) ch[j] = Xc1 * Qr[j];
+            Cc1 = chunk_reduce(red, l, ch);
+          }
         }
       }
       zl = yl;
