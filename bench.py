@@ -473,6 +473,39 @@ def main_b200(args):
     else:
         per_rank_ms = [float(per_rank.item())]
 
+    # N > 1: the same episodes once more with EVERY rank on rank 0's draw.  The ranks' own draws differ
+    # (seed + rank) and a launch lasts as long as its slowest quarter, so the max over ranks mixes "what
+    # does a second process cost" with "how heavy is the worst draw"; this leg separates the two.
+    same_draw = None
+    if world > 1:
+        rs0 = np.random.default_rng(20240601)
+        x0_0 = rs0.uniform(-2, 2, (S, 2))
+        xref_0 = np.stack([rs0.uniform(-1, 1, S), np.zeros(S)], axis=1)
+        loop0 = K.ClosedLoop(K.vanderpol_spec(), torch.from_numpy(x0_0).to(dev), gold["A"], gold["B"], gold["C"],
+                             enc(torch.from_numpy(xref_0).to(dev)), encoder=enc, log_steps=T)
+        loop0.reset().run(T)
+        barrier()
+        s0 = [torch.cuda.Event(enable_timing=True) for _ in range(Kst)]
+        s1 = [torch.cuda.Event(enable_timing=True) for _ in range(Kst)]
+        for k in range(Kst):
+            loop0.reset()
+            flush.zero_()
+            s0[k].record()
+            loop0.run(T)
+            s1[k].record()
+        barrier()
+        ms0 = sum(a.elapsed_time(b) for a, b in zip(s0, s1))
+        mine0 = torch.tensor([ms0 / Kst], dtype=torch.float64, device=dev)
+        all0 = [torch.empty_like(mine0) for _ in range(world)]
+        dist.all_gather(all0, mine0)
+        ms0_max = D.max_over_ranks(ms0, dev)
+        same_draw = {"value": world * S * T * Kst / (ms0_max * 1e-3), "unit": UNIT,
+                     "per_rank_ms": [float(t.item()) for t in all0],
+                     "note": "every rank runs rank 0's draw (seed 20240601): isolates the cost of N processes from "
+                             "the spread between the ranks' own draws"}
+        loop0.close()
+        del loop0
+
     # the steady-state tail of the same loop (steps T .. 2T: no restart transient, no switch)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -571,6 +604,7 @@ def main_b200(args):
                                      "carries only x0/model in, logs and final state out"},
             },
             "per_rank_ms": per_rank_ms,
+            "same_draw": same_draw,
             "value_steady_state": world * S * T / (ms_steady * 1e-3),
             "us_per_closed_loop_step": ms_step * 1e3 / T,
             "cpu_baseline": cpu,
