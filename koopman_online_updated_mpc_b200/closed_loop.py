@@ -46,7 +46,7 @@ class LoopSpec:
     q0: float = 100.0              # duffing.py:946
     tol: float = 0.0
     path: int = PATH_AUTO          # PATH_GENERIC: force the per-step generic kernels (cross-check of the fused one)
-    qp_cold: int = 0               # generic kernels: 0 warm start + sweeps, 1 cold start (duffing.py:634), 2 warm primal only
+    qp_cold: int = 0               # generic kernels: 0 warm start + sweeps, 1 cold start (duffing.py:634), 2 warm primal only, 3 warm + undamped sweeps
     params_pre: tuple = _plant.DUFFING_PRE
     params_post: tuple = _plant.DUFFING_POST
 

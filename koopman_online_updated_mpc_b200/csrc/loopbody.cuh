@@ -86,7 +86,7 @@ KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, const LoopShape sh, int64
     KMPC_LANE_LOOP(i, N) ws.x[i] = (i + 1 < N) ? xp[i + 1] : (sh.du_aug ? 0.0 : xp[i]);
     KMPC_SYNCWARP();
   }
-  const int st = qp_solve_warp<G>(ws, N, c.max_iter, c.tol, warm, c.qp_cold != 2);
+  const int st = qp_solve_warp<G>(ws, N, c.max_iter, c.tol, warm, c.qp_cold != 2, G == 32 && c.qp_cold != 3);
   if (d.qp_x != nullptr && valid) {
     const bool ok = !(st & (KMPC_STATUS_NONFINITE | KMPC_STATUS_MAXITER));   // else: cold start next step
     KMPC_LANE_LOOP(i, N) d.qp_x[s * N + i] = ok ? ws.x[i] : NAN;
