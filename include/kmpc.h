@@ -208,8 +208,11 @@ typedef struct kmpc_loop_config {
   int qp_cold;         /* generic kernels: 0 = warm start from the previous step's moves, primal-dual sweeps then
                           the primal method (same minimiser as a cold start); 1 = cold-start every QP like the
                           reference (duffing.py:634: pastRes is never written back); 2 = warm start, primal
-                          method only (round-1 behaviour, kept for A/B timing); 3 = like 0 with undamped sweeps on
-                          the warp-per-scenario shapes (0 damps them there: one release per sweep; A/B timing) */
+                          method only (round-1 behaviour, kept for A/B timing); 3 = like 0 with DAMPED sweeps on the
+                          warp-per-scenario shapes (every violated bound is clipped but only the most negative
+                          multiplier is released per sweep, up to 40 sweeps): same minimiser, fewer factorisations
+                          where the plain sweeps cycle (Tank: -18 %); where the Hessian is numerically singular
+                          (cond > 1e16, flagged KMPC_STATUS_PIVOT) the iterate it stops at may differ from mode 0's */
 } kmpc_loop_config;
 
 typedef struct kmpc_loop_buffers {     /* all [dev] */

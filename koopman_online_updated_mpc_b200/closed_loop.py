@@ -46,7 +46,7 @@ class LoopSpec:
     q0: float = 100.0              # duffing.py:946
     tol: float = 0.0
     path: int = PATH_AUTO          # PATH_GENERIC: force the per-step generic kernels (cross-check of the fused one)
-    qp_cold: int = 0               # generic kernels: 0 warm start + sweeps, 1 cold start (duffing.py:634), 2 warm primal only, 3 warm + undamped sweeps
+    qp_cold: int = 0               # generic kernels: 0 warm start + sweeps, 1 cold start (duffing.py:634), 2 warm primal only, 3 warm + damped sweeps (Tank)
     params_pre: tuple = _plant.DUFFING_PRE
     params_post: tuple = _plant.DUFFING_POST
 
@@ -81,10 +81,11 @@ def rbf_spec(nz=8, **kw):
 
 def tank_spec(nz=10, **kw):
     """Tank_System.m: velocity form (l.110-113), N = 20, Q = 10, R = 1e-3 (l.116-118),
-    dU in +-0.5, u in +-8 (l.144-159), P0 = bar_Q0 = 1e4 I, switch tested before the plant call."""
+    dU in +-0.5, u in +-8 (l.144-159), P0 = bar_Q0 = 1e4 I, switch tested before the plant call.
+    qp_cold = 3: damped primal-dual sweeps (the plain sweeps cycle in more than half of this loop's heavy steps)."""
     return replace(LoopSpec(nz=nz, N=20, out_mode=OUT_C_ROW, out_row=1, du_aug=True, c_pairs_next=False,
                             skip_first_barx=True, plant_kind=_plant.PLANT_TANK, first_post_step=100,
-                            q=10.0, rw=1e-3, lb=-0.5, ub=0.5, p0=1e4, q0=1e4,
+                            q=10.0, rw=1e-3, lb=-0.5, ub=0.5, p0=1e4, q0=1e4, qp_cold=3,
                             params_pre=_plant.TANK_PRE, params_post=_plant.TANK_POST), **kw)
 
 

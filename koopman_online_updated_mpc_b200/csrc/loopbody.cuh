@@ -33,7 +33,7 @@ KMPC_HD inline LoopShape loop_shape(const kmpc_loop_config& c) {
 
 // QP + plant for scenario s at closed-loop step `step`; `base` = this group's smem slice;
 // `valid` = false for the padding groups of the last warp (compute, but write nothing).
-template <int G>
+template <int G, int NMAX = KMPC_MAX_HORIZON>
 KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, const LoopShape sh, int64_t s, bool valid,
                                      int64_t step, int64_t log_slot, double* base) {
   const kmpc_loop_config& c = d.c;
@@ -86,7 +86,7 @@ KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, const LoopShape sh, int64
     KMPC_LANE_LOOP(i, N) ws.x[i] = (i + 1 < N) ? xp[i + 1] : (sh.du_aug ? 0.0 : xp[i]);
     KMPC_SYNCWARP();
   }
-  const int st = qp_solve_warp<G>(ws, N, c.max_iter, c.tol, warm, c.qp_cold != 2, G == 32 && c.qp_cold != 3);
+  const int st = qp_solve_warp<G, NMAX>(ws, N, c.max_iter, c.tol, warm, c.qp_cold != 2, G == 32 && c.qp_cold == 3);
   if (d.qp_x != nullptr && valid) {
     const bool ok = !(st & (KMPC_STATUS_NONFINITE | KMPC_STATUS_MAXITER));   // else: cold start next step
     KMPC_LANE_LOOP(i, N) d.qp_x[s * N + i] = ok ? ws.x[i] : NAN;

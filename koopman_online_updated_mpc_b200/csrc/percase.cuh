@@ -410,9 +410,12 @@ constexpr int kQpSlotsMax = KMPC_MAX_HORIZON / 16;
 // compact rows c, c + G, ... and carries their original indices; the column owner broadcasts its
 // original index by shuffle.  ws.L / ws.invd hold the compact factor (nf(nf+1)/2 entries).
 // Loop trip counts use the maximum nf over the groups of the warp (the shuffles are warp-wide).
-template <int G>
+// NMAX: compile-time upper bound of the horizon (sizes the per-lane slots: a Tank QP, N = 20 on 32 lanes,
+// needs one slot, not the 64 / G of the run-time shape -- half the code, which matters because the single-warp
+// blocks of this kernel sit at unrelated program counters and live off the instruction cache).
+template <int G, int NMAX = KMPC_MAX_HORIZON>
 struct QpFreeMap {
-  static constexpr int SLOTS = KMPC_MAX_HORIZON / G;
+  static constexpr int SLOTS = (NMAX + G - 1) / G;
   int nf, nfw;       // free variables of this group / maximum over the groups of the warp
   int oi[SLOTS];     // original index of compact row lane + sl * G (-1 beyond nf)
   __device__ __forceinline__ void build(const QpWs& ws, int N) {
@@ -447,13 +450,11 @@ struct QpFreeMap {
   }
 };
 
-template <int G>
-__device__ __forceinline__ int qp_chol_masked_rows(const QpWs& ws, int N) {
-  constexpr int SLOTS = KMPC_MAX_HORIZON / G;
+template <int G, int NMAX>
+__device__ __forceinline__ int qp_chol_masked_rows(const QpWs& ws, int N, const QpFreeMap<G, NMAX>& fm) {
+  constexpr int SLOTS = QpFreeMap<G, NMAX>::SLOTS;
   const int lane = threadIdx.x & (G - 1);
   int status = 0;
-  QpFreeMap<G> fm;
-  fm.build(ws, N);
   const int nf = fm.nf;
 #pragma unroll
   for (int so = 0; so < SLOTS; ++so) {
@@ -507,12 +508,10 @@ __device__ __forceinline__ int qp_chol_masked_rows(const QpWs& ws, int N) {
   return status;
 }
 
-template <int G>
-__device__ __forceinline__ void qp_chol_solve_rows(const QpWs& ws, int N) {
-  constexpr int SLOTS = KMPC_MAX_HORIZON / G;
+template <int G, int NMAX>
+__device__ __forceinline__ void qp_chol_solve_rows(const QpWs& ws, int N, const QpFreeMap<G, NMAX>& fm) {
+  constexpr int SLOTS = QpFreeMap<G, NMAX>::SLOTS;
   const int lane = threadIdx.x & (G - 1);
-  QpFreeMap<G> fm;
-  fm.build(ws, N);
   const int nf = fm.nf;
   double pr[SLOTS];
 #pragma unroll
@@ -585,7 +584,9 @@ __device__ __forceinline__ void qp_gradient_rows(const QpWs& ws, int N) {
 template <int G>
 KMPC_DEV int qp_chol_masked(const QpWs& ws, int N) {
 #ifndef KMPC_HOSTEMU
-  return qp_chol_masked_rows<G>(ws, N);
+  QpFreeMap<G> fm;
+  fm.build(ws, N);
+  return qp_chol_masked_rows<G, KMPC_MAX_HORIZON>(ws, N, fm);
 #else
   int status = 0;
   for (int j = 0; j < N; ++j) {
@@ -628,7 +629,9 @@ KMPC_DEV int qp_chol_masked(const QpWs& ws, int N) {
 template <int G>
 KMPC_DEV void qp_chol_solve(const QpWs& ws, int N) {
 #ifndef KMPC_HOSTEMU
-  qp_chol_solve_rows<G>(ws, N);
+  QpFreeMap<G> fm;
+  fm.build(ws, N);
+  qp_chol_solve_rows<G, KMPC_MAX_HORIZON>(ws, N, fm);
 #else
   for (int j = 0; j < N; ++j) {  // forward, column oriented
     const double yj = ws.p[j] * ws.invd[j];
@@ -671,6 +674,23 @@ KMPC_DEV void qp_gradient(const QpWs& ws, int N) {
 #endif
 }
 
+// ws.p <- (2H)_FF^-1 ws.p on the free block F = {W == 0}: factorisation + both triangular solves with ONE
+// free-set map (W does not change in between).  Returns the factorisation's status bits.
+template <int G, int NMAX>
+KMPC_DEV int qp_factor_solve(const QpWs& ws, int N) {
+#ifndef KMPC_HOSTEMU
+  QpFreeMap<G, NMAX> fm;
+  fm.build(ws, N);
+  const int st = qp_chol_masked_rows<G, NMAX>(ws, N, fm);
+  qp_chol_solve_rows<G, NMAX>(ws, N, fm);
+  return st;
+#else
+  const int st = qp_chol_masked<G>(ws, N);
+  qp_chol_solve<G>(ws, N);
+  return st;
+#endif
+}
+
 // Exact solve of  min x'Hx + f'x,  lb <= x <= ub  (oracle/mpc.py solve_box_qp_exact is the same
 // algorithm).  Start: clipped unconstrained minimiser, clipped variables in the working set.
 // Iterations 0..kPdasIters-1 are primal-dual active-set sweeps (full Newton step on the free
@@ -694,7 +714,7 @@ constexpr int kPdasReleaseAll = 1;
 // a bound enters the working set, and the monotone primal method runs from there: when the optimal
 // set moves by a few bounds per step this costs a few factorisations, where a cold start needs
 // one per sweep and then one per bound of the final set whenever the sweeps cycle (Tank: 10 - 25).
-template <int G>
+template <int G, int NMAX = KMPC_MAX_HORIZON>
 KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol, bool warm = false,
                            bool warm_sweeps = true, bool damped = false) {
   int status = 0;
@@ -706,8 +726,7 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol, bool
       ws.p[i] = -ws.f[i];
     }
     KMPC_SYNCWARP();
-    status |= qp_chol_masked<G>(ws, N);
-    qp_chol_solve<G>(ws, N);
+    status |= qp_factor_solve<G, NMAX>(ws, N);
     KMPC_LANE_LOOP(i, N) {
       double xi = ws.p[i];
       int w = 0;
@@ -745,9 +764,8 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol, bool
     const bool pdas = (!warm || warm_sweeps) && it < (damped ? kPdasItersDamped : kPdasIters);  // uniform over the warp
     KMPC_LANE_LOOP(i, N) ws.p[i] = (ws.W[i] == 0) ? -ws.grad[i] : 0.0;
     KMPC_SYNCWARP();
-    const int cst = qp_chol_masked<G>(ws, N);
+    const int cst = qp_factor_solve<G, NMAX>(ws, N);
     if (!done) status |= cst;
-    qp_chol_solve<G>(ws, N);
     double alpha = 1.0;
     int block = 0x7fffffff;
     if (!pdas) {  // ratio test

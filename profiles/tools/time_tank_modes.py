@@ -1,5 +1,5 @@
 """A/B timing of the generic-path QP start modes on the Tank loop (BASELINE configs[2] shape) and the
-RBF horizon-50 loop: qp_cold = 0 (warm + damped primal-dual sweeps), 3 (warm + undamped sweeps), 2 (warm, primal only: round 1), 1 (cold)."""
+RBF horizon-50 loop: qp_cold = 3 (warm + damped primal-dual sweeps: tank_spec default), 0 (warm + plain sweeps), 2 (warm, primal only: round 1), 1 (cold)."""
 import json
 import os
 import sys
@@ -20,7 +20,7 @@ A, B, C, _ = SC.tank_identify(enc)
 x0 = np.maximum(np.random.default_rng(20240801).uniform(0, 2, (S, 2)), 0.0)
 out = {"S": S, "T": T}
 ref = None
-for mode in (0, 3, 2, 1):
+for mode in (3, 0, 2, 1):
     loop = K.ClosedLoop(replace(K.tank_spec(), qp_cold=mode), x0, A, B, C, np.array([1.0]), encoder=enc, log_steps=T)
     loop.run(T)
     torch.cuda.synchronize()
@@ -36,6 +36,6 @@ for mode in (0, 3, 2, 1):
         ref = lx
     ph = loop.reset().run_timed(min(T, 300))
     out["mode%d" % mode] = {"ms": ms, "scenario_steps_per_s": S * T / ms * 1e3, "status_nonzero": int((loop.status != 0).sum().item()),
-                            "max_abs_dx_vs_mode0": float(np.abs(lx - ref).max()), "phase_ms": ph}
+                            "max_abs_dx_vs_first_mode": float(np.abs(lx - ref).max()), "phase_ms": ph}
     loop.close()
 print(json.dumps(out))
