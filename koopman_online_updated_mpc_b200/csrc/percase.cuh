@@ -556,6 +556,31 @@ __device__ __forceinline__ void qp_chol_solve_rows(const QpWs& ws, int N, const 
   __syncwarp();
 }
 
+// Compile-time horizon bound (Tank: 20, horizon 50): branch-free walk over the packed triangle --
+// H[i][j] sits at T(i) + j for j <= i and at T(j) + i above the diagonal, T(j) a constant after unrolling.
+template <int G, int NMAX>
+__device__ __forceinline__ void qp_gradient_rows_ct(const QpWs& ws, int N) {
+  const int lane = threadIdx.x & (G - 1);
+#pragma unroll
+  for (int sl = 0; sl < (NMAX + G - 1) / G; ++sl) {
+    const int i = lane + sl * G;
+    if (i < N) {
+      const int ti = tri(i, 0);
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < NMAX; ++j) {
+        if (j < N) {
+          const double h = ws.H[(i >= j) ? ti + j : (j * (j + 1)) / 2 + i];
+          if (j & 1) s1 = fma(h, ws.x[j], s1);
+          else s0 = fma(h, ws.x[j], s0);
+        }
+      }
+      ws.grad[i] = 2.0 * (s0 + s1) + ws.f[i];
+    }
+  }
+  __syncwarp();
+}
+
 template <int G>
 __device__ __forceinline__ void qp_gradient_rows(const QpWs& ws, int N) {
   const int lane = threadIdx.x & (G - 1);
@@ -660,10 +685,11 @@ KMPC_DEV void qp_chol_solve(const QpWs& ws, int N) {
 }
 
 // grad = 2 H x + f
-template <int G>
+template <int G, int NMAX = KMPC_MAX_HORIZON>
 KMPC_DEV void qp_gradient(const QpWs& ws, int N) {
 #ifndef KMPC_HOSTEMU
-  qp_gradient_rows<G>(ws, N);
+  if (NMAX < KMPC_MAX_HORIZON) qp_gradient_rows_ct<G, NMAX>(ws, N);
+  else qp_gradient_rows<G>(ws, N);
 #else
   KMPC_LANE_LOOP(i, N) {
     double s = 0.0;
@@ -756,7 +782,7 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol, bool
   KMPC_SYNCWARP();
   const double mtol = tol * fmax(1.0, fmaxabs);
   bool done = !any;
-  if (warp_any(!done)) qp_gradient<G>(ws, N);  // grad at the start point; refreshed after each step
+  if (warp_any(!done)) qp_gradient<G, NMAX>(ws, N);  // grad at the start point; refreshed after each step
   for (int it = 0; it < max_iter; ++it) {
     if (!warp_any(!done)) break;
     // primal-dual sweeps first, also from a warm working set (a good guess converges in 1 - 3 sweeps where
@@ -797,7 +823,7 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol, bool
       }
     }
     KMPC_SYNCWARP();
-    qp_gradient<G>(ws, N);  // at the new point (PDAS: the unclipped face minimiser)
+    qp_gradient<G, NMAX>(ws, N);  // at the new point (PDAS: the unclipped face minimiser)
     if (pdas) {
       int changed = 0, clipped = 0;
       const bool single = damped && it >= kPdasReleaseAll;   // uniform over the warp
@@ -842,7 +868,7 @@ KMPC_DEV int qp_solve_warp(const QpWs& ws, int N, int max_iter, double tol, bool
       changed = group_or<G>(changed) | clipped;
       if (!done && !changed) done = true;
       KMPC_SYNCWARP();
-      if (warp_any(clipped != 0)) qp_gradient<G>(ws, N);
+      if (warp_any(clipped != 0)) qp_gradient<G, NMAX>(ws, N);
     } else {
       // after a full step: multipliers of the bound variables
       double worst = INFINITY;
