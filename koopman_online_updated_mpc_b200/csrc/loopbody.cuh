@@ -131,11 +131,11 @@ KMPC_DEV void loop_rls_scenario(const LoopDev& d, const int nz, int64_t s, bool 
     KMPC_LANE_LOOP(e, n * nz) ws.barX[e] = 0.0;
     KMPC_LANE_LOOP(e, nz * nz) ws.barQ[e] = (e / nz == e % nz) ? c.q0 : 0.0;
   } else {
-    KMPC_LANE_LOOP(e, nz * nv) ws.KA[e] = d.b.KA[s * nz * nv + e];
-    KMPC_LANE_LOOP(e, nv * nv) ws.P[e] = d.b.P[s * nv * nv + e];
+    KMPC_COPY_G2S(ws.KA, d.b.KA + s * nz * nv, nz * nv);
+    KMPC_COPY_G2S(ws.P, d.b.P + s * nv * nv, nv * nv);
     if (upc) {
-      KMPC_LANE_LOOP(e, n * nz) ws.barX[e] = d.b.barX[s * n * nz + e];
-      KMPC_LANE_LOOP(e, nz * nz) ws.barQ[e] = d.b.barQ[s * nz * nz + e];
+      KMPC_COPY_G2S(ws.barX, d.b.barX + s * n * nz, n * nz);
+      KMPC_COPY_G2S(ws.barQ, d.b.barQ + s * nz * nz, nz * nz);
     }
   }
   // the RLS state above is not touched by the QP / lift kernels of this step, so it was loaded
@@ -147,6 +147,7 @@ KMPC_DEV void loop_rls_scenario(const LoopDev& d, const int nz, int64_t s, bool 
   }
   if (KMPC_LANE0) ws.v[nz] = d.b.u_prev[s];
   KMPC_LANE_LOOP(e, n) ws.xc[e] = c.c_pairs_next ? d.b.x[s * n + e] : d.x_prev[s * n + e];
+  KMPC_COPY_G2S_WAIT();
   KMPC_SYNCWARP();
   int flags = c.rls_flags;
   if (first && c.skip_first_barx) flags |= KMPC_RLS_SKIP_BARX;

@@ -31,6 +31,8 @@ inline double rsqrt(double v) { return 1.0 / sqrt(v); }
 #define KMPC_LANE0 true
 #define KMPC_UNROLL
 #define KMPC_PDL_WAIT() ((void)0)
+#define KMPC_COPY_G2S(dst, src, n) KMPC_LANE_LOOP(e_, n) (dst)[e_] = (src)[e_]
+#define KMPC_COPY_G2S_WAIT() ((void)0)
 #else
 #define KMPC_DEV __device__ __forceinline__
 #define KMPC_HD __host__ __device__
@@ -47,6 +49,14 @@ inline double rsqrt(double v) { return 1.0 / sqrt(v); }
     asm volatile("griddepcontrol.wait;" ::: "memory");           \
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
   } while (0)
+// global -> shared copy of n doubles by the lanes of a group without staging in registers (cp.async, SASS
+// LDGSTS): every element of every array is in flight at once, the latency is paid once at the wait
+#define KMPC_COPY_G2S(dst, src, n)                                                                     \
+  KMPC_LANE_LOOP(e_, n)                                                                                \
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared((dst) + e_)), \
+               "l"((src) + e_)                                                                         \
+               : "memory")
+#define KMPC_COPY_G2S_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 #endif
 
 namespace kmpc {
@@ -193,9 +203,16 @@ KMPC_DEV void rls_update_warp(const RlsWs& ws, int nz, int n, double lam, int fl
   double vPv = 0.0;  // (v'P) v, duffing.py:934
   KMPC_UNROLL for (int j = 0; j < nv; ++j) vPv += ws.rrow[j] * ws.v[j];
   const double denom = lam + vPv;
-  KMPC_LANE_LOOP(e, nv * nv) {
-    int i = e / nv, j = e - i * nv;
-    ws.P[e] = ws.P[e] / lam - (ws.w[i] * ws.rrow[j]) / lam / denom;
+  if (lam == 1.0) {  // x / 1 == x exactly: the same bits with one division per entry instead of three
+    KMPC_LANE_LOOP(e, nv * nv) {
+      int i = e / nv, j = e - i * nv;
+      ws.P[e] = ws.P[e] - (ws.w[i] * ws.rrow[j]) / denom;
+    }
+  } else {           // Koopman_update.m:270 forgetting factor
+    KMPC_LANE_LOOP(e, nv * nv) {
+      int i = e / nv, j = e - i * nv;
+      ws.P[e] = ws.P[e] / lam - (ws.w[i] * ws.rrow[j]) / lam / denom;
+    }
   }
   KMPC_LANE_LOOP(e, nz * nv) {
     int i = e / nv, j = e - i * nv;

@@ -27,6 +27,13 @@ S = int(sys.argv[1]) if len(sys.argv) > 1 else 125000
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 x0 = np.random.default_rng(20240901).uniform(-2, 2, (S, 2))
 warm = K.RLSState.warm(S, G, Aq, XV[:, :8], G[:8, :8])
-loop = K.ClosedLoop(K.rbf_spec(N=50), x0, Ar, Br, Cr, np.array([1.0, 0.0]), cx=cx_d, rls_state=warm, log_steps=0)
+mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+loop = K.ClosedLoop(K.rbf_spec(N=50, qp_cold=mode), x0, Ar, Br, Cr, np.array([1.0, 0.0]), cx=cx_d, rls_state=warm, log_steps=0)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
 loop.run(T)
+e1.record()
 torch.cuda.synchronize()
+ms = e0.elapsed_time(e1)
+print("rbf horizon 50, S=%d, T=%d, qp_cold=%d: %.1f ms, %.2f M scenario-steps/s, scenarios with status %d"
+      % (S, T, mode, ms, S * T / ms / 1e3, int((loop.status != 0).sum().item())))
