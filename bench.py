@@ -419,7 +419,19 @@ def main_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        # ... including NCCL's own "NCCL version" banner, which it writes to fd 1 when the first communicator
+        # comes up: point fd 1 at stderr until that has happened
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -84,10 +84,11 @@ def test_tc_edmd_matches_reference_run():
 
 
 def test_tc_edmd_matches_fp64_path_at_scale():
-    """2 M synthetic duffing snapshots (20 000 trajectories x 100 steps, generated on the GPU like
-    data_generate.py:17-57): the Koopman matrices from the tcgen05 lift agree with the fp64 lift."""
+    """BASELINE configs[3] size: 10 M synthetic duffing snapshots (100 000 trajectories x 100 steps, generated
+    on the GPU like data_generate.py:17-57): the Koopman matrices from the tcgen05 lift agree with the fp64
+    lift to the north-star tolerance (1e-4 relative)."""
     enc, _, _ = _enc("duffing")
-    n_traj, n_step = 20000, 100
+    n_traj, n_step = 100000, 100
     rs = np.random.default_rng(7)
     X, Y, U = K.data_generate.generate_snapshots(rs.uniform(-2, 2, (n_traj, 2)), rs.uniform(-2, 2, (n_step, n_traj)),
                                                  K.plant.DUFFING_PRE)
