@@ -41,6 +41,19 @@ def main():
     gr = H.golden("ref_duffing_rbf.npz")
     K.ClosedLoop(K.rbf_spec(N=50, update=False), rs.uniform(-2, 2, (9, 2)), gr["A"], gr["B"], gr["C"],
                  np.array([1.0, 0.0]), cx=gr["cx"], log_steps=3).run(3)   # N = 50: two row slots per lane
+    K.ClosedLoop(K.duffing_spec(), rs.uniform(-1.5, 1.5, (12, 2)), gd["A"], gd["B"], gd["C"], np.array([1.0, 0.0]),
+                 encoder=encd, log_steps=5).run(3).run(2)                  # fused, update, y = C z, chunked (warm-start state)
+    Xs, Ys, Us = DG.generate(20, 20).duffing_generate()
+    cxd = torch.from_numpy(gr["cx"]).cuda()
+    pkr = E.gram_accumulate(K.lift.rbf(torch.from_numpy(Xs.T.copy()).cuda(), cxd), K.lift.rbf(torch.from_numpy(Ys.T.copy()).cuda(), cxd),
+                            Us.reshape(-1), Xs.T.copy()).cpu().numpy()
+    Gm, Aq, XV = pkr[:81].reshape(9, 9), pkr[81:153].reshape(8, 9), pkr[153:171].reshape(2, 9)
+    warm = K.RLSState.warm(5, Gm, Aq, XV[:, :8], Gm[:8, :8])
+    K.ClosedLoop(K.rbf_spec(N=50), rs.uniform(-2, 2, (5, 2)), gr["A"], gr["B"], gr["C"], np.array([1.0, 0.0]),
+                 cx=gr["cx"], rls_state=warm, log_steps=3).run(3)          # N = 50 with the warm-started update (cp.async RLS loads)
+    if os.environ.get("KMPC_SANITIZE_TC", "1") == "1" and encd.has_tc:
+        ztc = encd(rs.uniform(-2, 2, (300, 2)), precision=K.lift.PREC_TC)  # tcgen05 / TMEM / TMA lift, three tiles, ragged
+        assert bool(np.isfinite(np.asarray(ztc.cpu() if hasattr(ztc, "cpu") else ztc)).all())
     X, Y, U = DG.generate_snapshots(rs.uniform(-1, 1, (37, 2)), rs.uniform(-2, 2, (11, 37)), K.plant.DUFFING_PRE)
     pk = E.gram_from_trajectories(encd, X, Y, U, 11)
     A, B, C, st = E.edmd_solve(E.gram_from_snapshots(encd, X, Y, U), 8)
