@@ -89,6 +89,111 @@ gram_kernel(const double* __restrict__ psi, const double* __restrict__ psin,
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(pack + NR * NV, (double)M);   // snapshot count (exact)
 }
 
+// nz = 8, n = 2 on the fp64 tensor path (mma.sync m8n8k4 f64, SASS DMMA): the Gram is the skinny GEMM
+// R V' with K = snapshots.  A warp walks groups of 4 snapshots (one k-step): lane (gid, tig) = (component,
+// snapshot in the group) loads ONE double of the lifted state and one of its successor -- a group is 256
+// contiguous bytes of each -- and these registers are at once the A fragments of the row tiles
+// [z], [z+], [u, x1, x2, 0...] and the B fragments of the column tiles [z], [u, 0...]: six DMMAs per
+// group, no shared memory, 12 accumulator doubles per lane for the whole launch.  fp64 accumulation
+//  on 24 pipe cycles per snapshot and sub-partition instead of 171 FMAs + 60 loads per
+// snapshot on CUDA cores.
+__device__ __forceinline__ void gram_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int kGramDmmaWarps = 8;
+
+__global__ void __launch_bounds__(kGramDmmaWarps * 32, 2)
+gram_dmma_kernel(const double* __restrict__ psi, const double* __restrict__ psin, const double* __restrict__ u,
+                 const double* __restrict__ x, int64_t M, double* __restrict__ pack, int seg) {
+  constexpr int NZ = 8, NV = 9, NR = 19;
+  __shared__ double red[NR * NV];
+  for (int e = threadIdx.x; e < NR * NV; e += blockDim.x) red[e] = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int64_t warp = (int64_t)blockIdx.x * kGramDmmaWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kGramDmmaWarps;
+  const int64_t groups = (M + 3) >> 2;
+  // a warp owns a CONTIGUOUS range of groups (streaming reads; the trajectory index of the lane's snapshot
+  // advances incrementally: one division per lane and launch instead of one per group)
+  const int64_t per = (groups + nwarps - 1) / nwarps;
+  const int64_t g0 = warp * per, g1 = (g0 + per < groups) ? g0 + per : groups;
+  double c[3][2][2];
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int n = 0; n < 2; ++n) c[t][n][0] = c[t][n][1] = 0.0;
+  int64_t m = 4 * g0 + tig;                 // this lane's snapshot of the group being LOADED
+  int64_t traj = seg ? m / seg : 0;
+  int off = seg ? (int)(m - traj * seg) : 0;
+  int64_t gl = g0;                          // group being loaded
+  // fragments of the next group; snapshots beyond M (or beyond the warp's range) contribute zeros
+  auto load = [&](double& az, double& an, double& am) {
+    az = an = am = 0.0;
+    if (gl < g1 && m < M) {
+      const int64_t pr = m + traj;          // trajectory layout: seg + 1 consecutive states per trajectory
+      az = __ldg(psi + pr * NZ + gid);
+      an = __ldg((seg ? psi + (pr + 1) * NZ : psin + m * NZ) + gid);
+      if (gid == 0) am = __ldg(u + m);
+      else if (gid < 3) am = __ldg(x + m * 2 + (gid - 1));
+    }
+    ++gl;
+    m += 4;
+    if (seg) {
+      off += 4;
+      while (off >= seg) {
+        off -= seg;
+        ++traj;
+      }
+    }
+  };
+  auto mult = [&](double az, double an, double am) {
+    const double b1 = (gid == 0) ? am : 0.0;
+    gram_dmma(c[0][0][0], c[0][0][1], az, az);
+    gram_dmma(c[1][0][0], c[1][0][1], an, az);
+    gram_dmma(c[2][0][0], c[2][0][1], am, az);
+    gram_dmma(c[0][1][0], c[0][1][1], az, b1);
+    gram_dmma(c[1][1][0], c[1][1][1], an, b1);
+    gram_dmma(c[2][1][0], c[2][1][1], am, b1);
+  };
+  // four groups in flight per warp: the loads of groups g + 4 .. g + 7 fly while g .. g + 3 multiply
+  double f[4][3], h[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) load(f[k][0], f[k][1], f[k][2]);
+  for (int64_t g = g0; g < g1; g += 8) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) load(h[k][0], h[k][1], h[k][2]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mult(f[k][0], f[k][1], f[k][2]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) load(f[k][0], f[k][1], f[k][2]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mult(h[k][0], h[k][1], h[k][2]);
+  }
+  // accumulator (tile t, column tile n): lane holds rows gid, columns 2 tig, 2 tig + 1 -> pack positions
+  //   tile 0 = z rows -> G rows 0..7; tile 1 = z+ rows -> Aq rows; tile 2 = [u, x1, x2] -> G row 8, XV rows
+  //   column tile 0 = V columns 0..7, column tile 1 = column 8 (u) in its column 0
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int col = n ? 8 + 2 * tig + h : 2 * tig + h;
+        int row = -1;
+        if (t == 0) row = gid;
+        else if (t == 1) row = NV + gid;
+        else if (gid == 0) row = 8;
+        else if (gid < 3) row = NV + NZ + gid - 1;
+        if (row >= 0 && col < NV) atomicAdd(&red[row * NV + col], c[t][n][h]);
+      }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NR * NV; e += blockDim.x) atomicAdd(pack + e, red[e]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(pack + NR * NV, (double)M);   // snapshot count (exact)
+}
+
 // Generic path (any nz <= KMPC_MAX_NZ): one thread per output element and block-strided
 // snapshots; used for dimensions without a specialised instantiation.
 __global__ void gram_generic_kernel(const double* __restrict__ psi, const double* __restrict__ psin,
@@ -172,7 +277,10 @@ int gram_accumulate_impl(const double* psi, const double* psi_next, const double
   int64_t want = (M + 63) / 64;
   const unsigned grid = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
   if (nz == 8 && n == 2) {
-    gram_kernel<8, 2><<<grid, 64 * 3, 0, st>>>(psi, psi_next, u, x, M, pack, seg);
+    // CTAs of 8 warps, 2 resident per SM (98 registers: 12 accumulators + two sets of four prefetched groups), one wave
+    const int64_t want_w = ((M + 3) / 4 + 2 * kGramDmmaWarps - 1) / (2 * kGramDmmaWarps);
+    const unsigned gd = (unsigned)(want_w < (int64_t)sms * 2 ? (want_w > 0 ? want_w : 1) : (int64_t)sms * 2);
+    gram_dmma_kernel<<<gd, kGramDmmaWarps * 32, 0, st>>>(psi, psi_next, u, x, M, pack, seg);
     KMPC_AFTER_LAUNCH();
     return KMPC_OK;
   } else if (nz == 10 && n == 2) {
