@@ -475,6 +475,38 @@ def test_full_size_rbf_horizon50_properties():
     assert np.abs(o["X"] - lx[:, 0]).max() < 1e-7
 
 
+def test_generic_qp_start_modes_reach_the_same_minimiser():
+    """The QP has ONE minimiser (strictly convex): the generic kernels' start modes -- warm + sweeps (0),
+    cold like the reference (1), warm + primal only (2), warm + damped sweeps (3, tank_spec's default) --
+    differ in the path, not in the answer.  Horizon-50 RBF loop (frozen model and warm-started update,
+    well conditioned): identical trajectories to 1e-9; and the damped mode against the oracle."""
+    g = H.golden("ref_duffing_rbf.npz")
+    X, Y, U = oplant.generate_snapshots(100, 100, oplant.DUFFING_PRE, np.random.RandomState(101))
+    PX, PY = olift.rbf_lift(X.T, g["cx"]).T, olift.rbf_lift(Y.T, g["cx"]).T
+    G, Aq, XV = oedmd.gram_pack(PX, PY, U, X)
+    rs = np.random.default_rng(11)
+    S, T = 96, 25
+    x0 = rs.uniform(-2, 2, (S, 2))
+    for update in (False, True):
+        logs = {}
+        for mode in (0, 1, 2, 3):
+            warm = K.RLSState.warm(S, G, Aq, XV[:, :8], G[:8, :8]) if update else None
+            loop = K.ClosedLoop(K.rbf_spec(N=50, update=update, qp_cold=mode), x0, g["A"], g["B"], g["C"],
+                                np.array([1.0, 0.0]), cx=g["cx"], rls_state=warm, log_steps=T).run(T)
+            assert not loop.fused and int(loop.status.max().item()) == 0
+            logs[mode] = (loop.log_x.cpu().numpy(), loop.log_u.cpu().numpy())
+        for mode in (1, 2, 3):
+            assert np.abs(logs[mode][0] - logs[0][0]).max() < 1e-9, (update, mode)
+            assert np.abs(logs[mode][1] - logs[0][1]).max() < 1e-8, (update, mode)
+    cfg = ocl.rbf_config(g["cx"])
+    cfg.N = 50
+    for s in range(3):
+        o = ocl.run_loop(cfg, g["A"], g["B"], g["C"], x0[s], T, update=ocl.UPDATE_RLS, qp="exact",
+                         warm=orls.RLSState.warm(G, Aq, XV[:, :8], G[:8, :8]))
+        assert np.abs(o["X"] - logs[3][0][:, s]).max() < 1e-7, s
+        assert np.abs(o["U"] - logs[3][1][:, s]).max() < 1e-6, s
+
+
 # ------------------------------------------- snapshot generator + open-loop predictor (N1, N2) --
 @pytest.mark.parametrize("name,seed", [("duffing", 33), ("vanderpol", 50)])
 def test_snapshot_generator_matches_oracle_and_reference_run(name, seed):
