@@ -489,6 +489,53 @@ struct QpFreeMap {
   }
 };
 
+// Horizon-50 shape (one scenario per warp, two row slots per lane): the k < j0 part of the dot products of a
+// whole panel of 8 columns j0 .. j0 + 7 is ONE small GEMM, S = L[j0.., 0..j0) L[j0..j0+8, 0..j0)', done on the fp64
+// tensor path before the panel's columns are eliminated: a DMMA (m8n8k4) does the work of 256 scalar FMAs with
+// two loads, its fragments come straight from the row-major factor (lane (gid, tig) reads L[row0 + gid][k0 + tig]),
+// and S is parked in the panel's own -- not yet written -- entries of L.  The column steps then only add the
+// k in [j0, j) terms.  45 % of this kernel's samples were those dot products.
+__device__ __forceinline__ void qp_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+template <int NMAX>
+__device__ __forceinline__ void qp_chol_panel_dmma(const QpWs& ws, int nf, int j0) {
+  constexpr int MAXB = (NMAX + 7) / 8;
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int nb = (nf + 7) >> 3, jb = j0 >> 3;
+  double c[MAXB][2];
+#pragma unroll
+  for (int t = 0; t < MAXB; ++t) c[t][0] = c[t][1] = 0.0;
+  const int rb = j0 + gid;
+  const double* prow = ws.L + lidx<NMAX>(rb < nf ? rb : 0, tig);
+  for (int k0 = 0; k0 < j0; k0 += 4) {
+    const double b = (rb < nf) ? prow[k0] : 0.0;
+    qp_dmma(c[0][0], c[0][1], b, b);          // the panel's own row block: A = B
+#pragma unroll
+    for (int t = 1; t < MAXB; ++t) {
+      if (jb + t < nb) {                        // warp-uniform
+        const int ra = 8 * (jb + t) + gid;
+        const double a = (ra < nf) ? ws.L[lidx<NMAX>(ra, k0 + tig)] : 0.0;
+        qp_dmma(c[t][0], c[t][1], a, b);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < MAXB; ++t) {
+    if (jb + t < nb) {
+      const int row = 8 * (jb + t) + gid;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int col = j0 + 2 * tig + h;
+        if (row < nf && col <= row) ws.L[lidx<NMAX>(row, col)] = c[t][h];
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int G, int NMAX>
 __device__ __forceinline__ int qp_chol_masked_rows(const QpWs& ws, int N, const QpFreeMap<G, NMAX>& fm) {
   constexpr int SLOTS = QpFreeMap<G, NMAX>::SLOTS;
@@ -500,10 +547,14 @@ __device__ __forceinline__ int qp_chol_masked_rows(const QpWs& ws, int N, const 
     for (int j = so * G; j < fm.nfw && j < (so + 1) * G; ++j) {
       const int oj = __shfl_sync(0xffffffffu, fm.oi[so], j & (G - 1), G);   // -1 when j >= nf (another group's column)
       const bool live = j < nf;
+      constexpr bool PANELS = (G == 32) && (NMAX > 32) && (NMAX < KMPC_MAX_HORIZON);
+      const int kbeg = PANELS ? (j & ~7) : 0;   // first k the column step still has to add
+      if (PANELS && kbeg == j && j > 0 && live) qp_chol_panel_dmma<NMAX>(ws, nf, j);
       // dot products of row j with the rows below it, four accumulators per row (k mod 4, the tail into the
       // first: the summation order of every version of this kernel); row j's pairs are loaded once for all slots
-      const double* rowj = ws.L + lidx<NMAX>(j, 0);
+      const double* rowj = ws.L + lidx<NMAX>(j, kbeg);
       const double2* rj2 = reinterpret_cast<const double2*>(rowj);
+      const int jlen = j - kbeg;
       double sv[SLOTS], dmine = 1.0, acc[SLOTS][4];
       bool act[SLOTS];
       const double2* ri2[SLOTS];
@@ -511,9 +562,10 @@ __device__ __forceinline__ int qp_chol_masked_rows(const QpWs& ws, int N, const 
       for (int sl = 0; sl < SLOTS; ++sl) {
         const int i = lane + sl * G;
         act[sl] = live && i >= j && i < nf;
-        ri2[sl] = reinterpret_cast<const double2*>(ws.L + lidx<NMAX>(act[sl] ? i : j, 0));
+        ri2[sl] = reinterpret_cast<const double2*>(ws.L + lidx<NMAX>(act[sl] ? i : j, kbeg));
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[sl][q] = 0.0;
+        if (PANELS && kbeg > 0 && act[sl]) acc[sl][0] = ws.L[lidx<NMAX>(i, j)];   // S of the panel pre-pass
       }
       if (live && SLOTS == 1) {
         // short rows (Tank: 20 columns, 10 on average): scalar loads on four accumulators measured faster
@@ -521,16 +573,16 @@ __device__ __forceinline__ int qp_chol_masked_rows(const QpWs& ws, int N, const 
         if (act[0]) {
           const double* rowi = reinterpret_cast<const double*>(ri2[0]);
           int k = 0;
-          for (; k + 3 < j; k += 4) {
+          for (; k + 3 < jlen; k += 4) {
             acc[0][0] = fma(rowi[k], rowj[k], acc[0][0]);
             acc[0][1] = fma(rowi[k + 1], rowj[k + 1], acc[0][1]);
             acc[0][2] = fma(rowi[k + 2], rowj[k + 2], acc[0][2]);
             acc[0][3] = fma(rowi[k + 3], rowj[k + 3], acc[0][3]);
           }
-          for (; k < j; ++k) acc[0][0] = fma(rowi[k], rowj[k], acc[0][0]);
+          for (; k < jlen; ++k) acc[0][0] = fma(rowi[k], rowj[k], acc[0][0]);
         }
       } else if (live) {
-        const int blocks = j >> 2;
+        const int blocks = jlen >> 2;
         for (int bq = 0; bq < blocks; ++bq) {
           const double2 b0 = rj2[2 * bq], b1 = rj2[2 * bq + 1];
 #pragma unroll
@@ -544,7 +596,7 @@ __device__ __forceinline__ int qp_chol_masked_rows(const QpWs& ws, int N, const 
             }
           }
         }
-        for (int k = blocks << 2; k < j; ++k) {
+        for (int k = blocks << 2; k < jlen; ++k) {
           const double bk = rowj[k];
 #pragma unroll
           for (int sl = 0; sl < SLOTS; ++sl)
