@@ -16,7 +16,7 @@ ncu --set full --import-source on --clock-control none -k regex:tc_encoder --lau
     python profiles/tools/time_tc_lift.py 4000000 20000 > $OUT/ncu_tc.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:encoder_units --launch-skip 3 -c 1 -f -o $OUT/enc_units_full \
     python profiles/tools/time_tc_lift.py 4000000 20000 > $OUT/ncu_enc.log 2>&1
-ncu --set full --clock-control none -k regex:gram_kernel --launch-skip 3 -c 1 -f -o $OUT/gram_full \
+ncu --set full --clock-control none -k regex:gram_dmma --launch-skip 3 -c 1 -f -o $OUT/gram_full \
     python profiles/tools/time_tc_lift.py 4000000 20000 > $OUT/ncu_gram.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:loop_qp_plant --launch-skip 125 -c 1 -f -o $OUT/tank_qp_full \
     python profiles/tools/tank_profile_workload.py > $OUT/ncu_tank.log 2>&1
@@ -26,3 +26,6 @@ python profiles/tools/time_fused_chunks.py 4096 10 > $OUT/fused_chunk_profile.tx
 python profiles/tools/time_tank_modes.py 65536 300 > $OUT/tank_modes.json 2> $OUT/tank_modes.err
 python profiles/tools/time_tc_lift.py > $OUT/time_tc.json 2> $OUT/time_tc.err
 tail -2 $OUT/smoke.log
+ncu --set full --import-source on --clock-control none -k regex:loop_qp_plant --launch-skip 45 -c 1 -f -o $OUT/rbf50_qp_full \
+    python profiles/tools/rbf50_profile_workload.py > $OUT/ncu_rbf50.log 2>&1
+for m in 0 3 2 1; do python profiles/tools/rbf50_profile_workload.py 125000 100 $m | tail -1; done > $OUT/rbf50_modes.txt 2>&1
