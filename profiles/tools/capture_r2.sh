@@ -21,7 +21,7 @@ ncu --set full --clock-control none -k regex:gram_dmma --launch-skip 3 -c 1 -f -
 ncu --set full --import-source on --clock-control none -k regex:loop_qp_plant --launch-skip 125 -c 1 -f -o $OUT/tank_qp_full \
     python profiles/tools/tank_profile_workload.py > $OUT/ncu_tank.log 2>&1
 # probes
-./profiles/tools/fp64_mix_probe > $OUT/fp64_mix_probe.txt 2>&1
+(cd profiles/tools && nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o fp64_mix_probe fp64_mix_probe.cu) && ./profiles/tools/fp64_mix_probe > $OUT/fp64_mix_probe.txt 2>&1
 python profiles/tools/time_fused_chunks.py 4096 10 > $OUT/fused_chunk_profile.txt 2>&1
 python profiles/tools/time_tank_modes.py 65536 300 > $OUT/tank_modes.json 2> $OUT/tank_modes.err
 python profiles/tools/time_tc_lift.py > $OUT/time_tc.json 2> $OUT/time_tc.err
