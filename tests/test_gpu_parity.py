@@ -98,6 +98,41 @@ def test_gram_other_dimensions(nz):
     np.testing.assert_allclose(C, Co, atol=1e-10)
 
 
+@pytest.mark.parametrize("M", [1, 3, 4, 5, 1237, 148 * 2 * 8 * 8 * 4 + 3, 700001])
+def test_gram_tensor_path_ragged_sizes(M):
+    """nz = 8: the Gram runs on the fp64 tensor path (gram_dmma_kernel: groups of 4 snapshots, contiguous
+    ranges per warp, eight groups in flight).  Sizes around a group, around one group per warp and with
+    idle warps; pack and snapshot count against numpy."""
+    rs = np.random.RandomState(M % 1000)
+    PX, PY, U, X = rs.randn(8, M), rs.randn(8, M), rs.randn(1, M), rs.randn(2, M)
+    pack = K.edmd.gram_accumulate(PX.T.copy(), PY.T.copy(), U.ravel(), X.T.copy()).cpu().numpy()
+    G, Aq, XV = oedmd.gram_pack(PX, PY, U, X)
+    want = np.concatenate([G.ravel(), Aq.ravel(), XV.ravel()])
+    np.testing.assert_allclose(pack[:-1], want, rtol=0, atol=1e-12 * max(1.0, np.abs(want).max()) * max(1.0, M ** 0.5))
+    assert pack[-1] == M
+
+
+@pytest.mark.parametrize("n_step,n_traj", [(1, 7), (2, 5), (3, 9), (5, 13), (11, 37), (100, 211)])
+def test_gram_tensor_path_trajectory_layout(n_step, n_traj):
+    """Trajectory layout (n_step + 1 lifted states per trajectory, the snapshot's successor is the next row):
+    trajectories shorter than a group of 4, groups straddling trajectory boundaries."""
+    enc = K.Encoder.from_file(H.weights_path("duffing"))
+    rs = np.random.default_rng(n_step * 100 + n_traj)
+    X, Y, U = K.data_generate.generate_snapshots(rs.uniform(-2, 2, (n_traj, 2)), rs.uniform(-2, 2, (n_step, n_traj)),
+                                                 K.plant.DUFFING_PRE)
+    a = K.edmd.gram_from_trajectories(enc, X, Y, U, n_step, verify=True).cpu().numpy()
+    b = K.edmd.gram_from_snapshots(enc, X, Y, U).cpu().numpy()
+    Ws, bs = H.oracle_weights("duffing")
+    Xh, Yh = X.cpu().numpy(), Y.cpu().numpy()
+    G, Aq, XV = oedmd.gram_pack(olift.encoder_forward(Ws, bs, Xh).T, olift.encoder_forward(Ws, bs, Yh).T,
+                                U.cpu().numpy().reshape(1, -1), Xh.T)
+    want = np.concatenate([G.ravel(), Aq.ravel(), XV.ravel()])
+    tol = 1e-11 * max(1.0, np.abs(want).max())
+    np.testing.assert_allclose(a[:-1], want, rtol=0, atol=tol)
+    np.testing.assert_allclose(b[:-1], want, rtol=0, atol=tol)
+    assert a[-1] == b[-1] == n_step * n_traj
+
+
 def test_edmd_rank_deficient_is_flagged():
     rs = np.random.RandomState(0)
     PX = rs.randn(8, 500)
@@ -500,11 +535,12 @@ def test_generic_qp_start_modes_reach_the_same_minimiser():
             assert np.abs(logs[mode][1] - logs[0][1]).max() < 1e-8, (update, mode)
     cfg = ocl.rbf_config(g["cx"])
     cfg.N = 50
-    for s in range(3):
+    for s in range(8):   # the horizon-50 kernel factors with the DMMA panel pre-pass: held to the oracle directly
         o = ocl.run_loop(cfg, g["A"], g["B"], g["C"], x0[s], T, update=ocl.UPDATE_RLS, qp="exact",
                          warm=orls.RLSState.warm(G, Aq, XV[:, :8], G[:8, :8]))
-        assert np.abs(o["X"] - logs[3][0][:, s]).max() < 1e-7, s
-        assert np.abs(o["U"] - logs[3][1][:, s]).max() < 1e-6, s
+        for mode in (0, 3):
+            assert np.abs(o["X"] - logs[mode][0][:, s]).max() < 1e-7, (mode, s)
+            assert np.abs(o["U"] - logs[mode][1][:, s]).max() < 1e-6, (mode, s)
 
 
 # ------------------------------------------- snapshot generator + open-loop predictor (N1, N2) --
