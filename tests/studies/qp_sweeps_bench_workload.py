@@ -83,7 +83,7 @@ def warm_pdas(H, f, lb, ub, wlo, whi, tol=1e-10, pdas_iters=8, max_iter=120):
     return x, wlo, whi, it, hist
 
 POLICY = os.environ.get('POLICY', 'shift')
-def run(idx, seed=20240601, T=400, S=4096):
+def run(idx, seed=20240601 + int(os.environ.get("RANK", "0")), T=400, S=4096):
     noshift = False; prev = None; pol = 0; p2lo = np.zeros(10, bool); p2hi = np.zeros(10, bool)
     gold = np.load(GOLD)
     Ws, bs = ow.load_mat_encoder(WEIGHTS)
