@@ -158,6 +158,8 @@ int kmpc_ctx_create(kmpc_ctx** out, const kmpc_loop_config* cfg, const kmpc_loop
   if (c.out_mode < KMPC_OUT_C || c.out_mode > KMPC_OUT_C_ROW) return KMPC_ERR_ARG;
   if (c.out_mode == KMPC_OUT_C_ROW && (c.out_row < 0 || c.out_row >= c.n)) return KMPC_ERR_ARG;
   if (c.update && c.shared_model) return KMPC_ERR_ARG;  // online update needs per-scenario models
+  if (c.qp_cold < 0 || c.qp_cold > 3) return KMPC_ERR_ARG;   // kmpc.h: 0 .. 3
+  if (c.path != KMPC_PATH_AUTO && c.path != KMPC_PATH_GENERIC) return KMPC_ERR_ARG;
   if (!buf->x || !buf->z || !buf->u_prev || !buf->A || !buf->B || !buf->C || !buf->r ||
       !buf->params_pre || !buf->params_post)
     return KMPC_ERR_ARG;

@@ -79,6 +79,17 @@ def test_argument_validation_without_touching_the_gpu():
     assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 8, 2, 1, 10, 10, 10, 5, p, p, p, None) == -1   # rmse row out of range
     assert L.kmpc_open_loop_predict(p, p, p, p, p, p, 8, 2, 0, 10, 10, 10, 0, p, p, p, None) == 0    # no sequences
     assert L.kmpc_gram_from_trajectories(None, 0, p, p, p, 4, 10, p, None) == -1                      # no encoder
+    # closed-loop context: the explicit kernel-path / QP-start fields are range-checked before anything is allocated
+    from dataclasses import replace
+    import ctypes
+    from koopman_online_updated_mpc_b200 import _lib
+    from koopman_online_updated_mpc_b200.closed_loop import make_config, rbf_spec
+    buf = _lib.LoopBuffersC(**{k: p for k in ("x", "z", "u_prev", "A", "B", "C", "KA", "P", "barX", "barQ", "r",
+                                               "params_pre", "params_post", "cx")})
+    for bad in (dict(qp_cold=4), dict(qp_cold=-1), dict(path=7)):
+        cfg = make_config(replace(rbf_spec(), **bad), 4, False)
+        ctx = ctypes.c_void_p()
+        assert L.kmpc_ctx_create(ctypes.byref(ctx), ctypes.byref(cfg), ctypes.byref(buf), None, 0, None) == -1, bad
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
