@@ -42,7 +42,7 @@ loop_qp_plant_kernel(LoopDev d, int64_t step, int64_t log_slot) {
   const int nzq = sh.nz + sh.du_aug;
   const bool identity = sh.out_mode == KMPC_OUT_IDENTITY;
   const int ny = identity ? nzq : (sh.out_mode == KMPC_OUT_C ? 2 : 1);
-  loop_qp_plant_scenario<G, (N > 0 ? N : KMPC_MAX_HORIZON)>(d, sh, s, valid, step, log_slot,
+  loop_qp_plant_scenario<G, (N > 0 ? N : KMPC_MAX_HORIZON), (NZ > 0 ? NZ + DU : 0)>(d, sh, s, valid, step, log_slot,
                             smem + (size_t)group * qp_ws_doubles(nzq, ny, sh.N, identity));
 }
 

@@ -33,7 +33,7 @@ KMPC_HD inline LoopShape loop_shape(const kmpc_loop_config& c) {
 
 // QP + plant for scenario s at closed-loop step `step`; `base` = this group's smem slice;
 // `valid` = false for the padding groups of the last warp (compute, but write nothing).
-template <int G, int NMAX = KMPC_MAX_HORIZON>
+template <int G, int NMAX = KMPC_MAX_HORIZON, int NZQ = 0>
 KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, const LoopShape sh, int64_t s, bool valid,
                                      int64_t step, int64_t log_slot, double* base) {
   const kmpc_loop_config& c = d.c;
@@ -76,7 +76,7 @@ KMPC_DEV void loop_qp_plant_scenario(const LoopDev& d, const LoopShape sh, int64
     ws.ub[e] = hi;
   }
   KMPC_SYNCWARP();
-  qp_build_warp<G>(ws, nzq, ny, N, identity, c.q, c.rw, d.b.r + s * ny, 0, nullptr);
+  qp_build_warp<G, NZQ>(ws, nzq, ny, N, identity, c.q, c.rw, d.b.r + s * ny, 0, nullptr);
   // warm start: last step's optimal moves shifted by one (receding horizon; velocity form: the new
   // last move is "hold the input").  Uniform over the warp: one cold scenario makes its warp cold.
   bool warm = d.qp_x != nullptr;

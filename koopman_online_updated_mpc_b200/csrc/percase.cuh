@@ -339,13 +339,35 @@ KMPC_DEV QpWs qp_ws_carve(double* base, int nzq, int ny, int N, bool identity) {
 // Build H (packed) and f from the model in ws (A, B, Cy, z0) and the reference r.
 //   r_stride = 0: r is (ny) constant over the horizon; r_stride = ny: r is (N, ny).
 //   PN: optional terminal weight (ny*ny, row-major) replacing the last q*I block (nullable).
-template <int G>
+// NZQ > 0: compile-time model dimension -- the lane's row of A stays in registers over the N sequential
+// matvec steps (one load per FMA instead of two).
+template <int G, int NZQ = 0>
 KMPC_DEV void qp_build_warp(const QpWs& ws, int nzq, int ny, int N, bool identity, double q,
                             double rw, const double* r, int r_stride, const double* PN) {
   // ---- Krylov chains: VZ[t] = A VZ[t-1] (VZ[-1] = z0), VB[t+1] = A VB[t] (VB[0] = B);
   //      outputs 0..nzq-1 advance the z chain, nzq..2nzq-1 the B chain, in the same phase
   KMPC_LANE_LOOP(i, nzq) ws.VB[i] = ws.B[i];
   KMPC_SYNCWARP();
+#ifndef KMPC_HOSTEMU
+  if (NZQ > 0 && 2 * NZQ <= G) {   // one output per lane: lane o < NZQ advances the z chain, NZQ <= o < 2 NZQ the B chain
+    const int o = (int)(threadIdx.x & (G - 1));
+    const bool half = o >= NZQ, on = o < 2 * NZQ;
+    const int i = on ? (half ? o - NZQ : o) : 0;
+    double arow[NZQ > 0 ? NZQ : 1];
+#pragma unroll
+    for (int j = 0; j < NZQ; ++j) arow[j] = ws.A[i * NZQ + j];
+    for (int t = 0; t < N; ++t) {
+      if (on && (!half || t + 1 < N)) {
+        const double* src = half ? ws.VB + t * NZQ : ((t == 0) ? ws.z0 : ws.VZ + (t - 1) * NZQ);
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NZQ; ++j) s += arow[j] * src[j];
+        (half ? ws.VB + (t + 1) * NZQ : ws.VZ + t * NZQ)[i] = s;
+      }
+      __syncwarp();
+    }
+  } else
+#endif
   for (int t = 0; t < N; ++t) {
     KMPC_LANE_LOOP(o, 2 * nzq) {
       const int half = o >= nzq, i = half ? o - nzq : o;
