@@ -481,33 +481,34 @@ struct QpFreeMap {
   int oi[SLOTS];     // original index of compact row lane + sl * G (-1 beyond nf)
   __device__ __forceinline__ void build(const QpWs& ws, int N) {
     const int lane = threadIdx.x & (G - 1);
-    unsigned bits[SLOTS];
-    int cum[SLOTS + 1];
-    cum[0] = 0;
+    // every free variable knows its rank among the free ones (ballot + popc below its lane) and scatters its
+    // index to that slot of a small map -- ws.invd is dead until the factorisation that follows writes it --,
+    // lane c then reads the c-th free index back.  (Searching the n-th set bit with __fns was 6 % of the Tank
+    // kernel's instructions.)
+    int* cmap = reinterpret_cast<int*>(ws.invd);
+    int cum = 0;
 #pragma unroll
     for (int sl = 0; sl < SLOTS; ++sl) {
       const int i = lane + sl * G;
       const bool fr = (i < N) && (ws.W[i] == 0);
       unsigned b = __ballot_sync(0xffffffffu, fr);
       if (G < 32) b = (b >> (threadIdx.x & 31 & ~(G - 1))) & ((1u << G) - 1u);
-      bits[sl] = b;
-      cum[sl + 1] = cum[sl] + __popc(b);
+      if (fr) cmap[cum + __popc(b & ((1u << lane) - 1u))] = i;
+      cum += __popc(b);
     }
-    nf = cum[SLOTS];
+    nf = cum;
     nfw = nf;
     if (G < 32) {
 #pragma unroll
       for (int o = G; o < 32; o <<= 1) nfw = max(nfw, __shfl_xor_sync(0xffffffffu, nfw, o));
     }
+    __syncwarp();
 #pragma unroll
     for (int sl = 0; sl < SLOTS; ++sl) {
       const int c = lane + sl * G;
-      int o = -1;
-#pragma unroll
-      for (int s2 = 0; s2 < SLOTS; ++s2)
-        if (c >= cum[s2] && c < cum[s2 + 1]) o = s2 * G + (int)__fns(bits[s2], 0, c - cum[s2] + 1);
-      oi[sl] = o;
+      oi[sl] = (c < nf) ? cmap[c] : -1;
     }
+    __syncwarp();   // the map has been read: the factorisation may write ws.invd
   }
 };
 
@@ -764,15 +765,14 @@ __device__ __forceinline__ void qp_gradient_rows(const QpWs& ws, int N) {
 }
 #endif  // !KMPC_HOSTEMU
 
+#ifdef KMPC_HOSTEMU
+// Host-emulator forms (lane loops).  The device goes through qp_factor_solve below: ONE free-set map for the
+// factorisation and both solves (the map is staged in ws.invd, which the factorisation then overwrites, so the
+// two halves cannot be called separately there).
 // Cholesky of the free block of 2H into ws.L (masked rows/cols become identity rows).
 // Returns KMPC_STATUS_PIVOT if a pivot was not positive.
 template <int G>
 KMPC_DEV int qp_chol_masked(const QpWs& ws, int N) {
-#ifndef KMPC_HOSTEMU
-  QpFreeMap<G> fm;
-  fm.build(ws, N);
-  return qp_chol_masked_rows<G, KMPC_MAX_HORIZON>(ws, N, fm);
-#else
   int status = 0;
   for (int j = 0; j < N; ++j) {
     const bool mj = ws.W[j] != 0;  // warp-uniform
@@ -807,17 +807,11 @@ KMPC_DEV int qp_chol_masked(const QpWs& ws, int N) {
     KMPC_SYNCWARP();
   }
   return status;
-#endif
 }
 
 // Solve (L L') p = rhs in place in ws.p (rhs must be zero on masked entries).
 template <int G>
 KMPC_DEV void qp_chol_solve(const QpWs& ws, int N) {
-#ifndef KMPC_HOSTEMU
-  QpFreeMap<G> fm;
-  fm.build(ws, N);
-  qp_chol_solve_rows<G, KMPC_MAX_HORIZON>(ws, N, fm);
-#else
   for (int j = 0; j < N; ++j) {  // forward, column oriented
     const double yj = ws.p[j] * ws.invd[j];
     KMPC_SYNCWARP();
@@ -841,8 +835,8 @@ KMPC_DEV void qp_chol_solve(const QpWs& ws, int N) {
     }
     KMPC_SYNCWARP();
   }
-#endif
 }
+#endif  // KMPC_HOSTEMU
 
 // grad = 2 H x + f
 template <int G, int NMAX = KMPC_MAX_HORIZON>
