@@ -132,18 +132,6 @@ __device__ __forceinline__ void group_gather(double* ex, int l, double mine, dou
 //   factor_solve: Cholesky of the free block of 2H with the right-hand side carried along, done by
 //   every lane redundantly in registers (no exchange, no synchronisation), which leaves the step p
 //   replicated in registers.
-// 1 / sqrt(d) for a positive normal d (the pivots are floored above zero; NaN propagates): hardware
-// seed (MUFU.RSQ64H, ~2^-26 relative) and one third-order correction y (1 + e/2 + 3 e^2/8), e = 1 - d y^2,
-// which leaves ~2^-78 before the final rounding -- the accuracy of rsqrt() without its special-case paths.
-__device__ __forceinline__ double rsqrt_pos(double d) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  const double t = d * y;
-  const double e = fma(-t, y, 1.0);
-  const double c = fma(0.375, e, 0.5);
-  return fma(y, e * c, y);
-}
-
 struct QpCoop {
   const double* HF;   // packed lower 2H (55) | f (10)
   double* sc;         // Lc (60) | xs (10) | gs (10)

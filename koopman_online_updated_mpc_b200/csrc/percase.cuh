@@ -451,6 +451,18 @@ KMPC_DEV void qp_build_warp(const QpWs& ws, int nzq, int ny, int N, bool identit
 }
 
 #ifndef KMPC_HOSTEMU
+// 1 / sqrt(d) for a positive normal d (the pivots are floored above zero; NaN propagates): hardware
+// seed (MUFU.RSQ64H, ~2^-26 relative) and one third-order correction y (1 + e/2 + 3 e^2/8), e = 1 - d y^2,
+// which leaves ~2^-78 before the final rounding -- the accuracy of rsqrt() without its special-case paths.
+__device__ __forceinline__ double rsqrt_pos(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double t = d * y;
+  const double e = fma(-t, y, 1.0);
+  const double c = fma(0.375, e, 0.5);
+  return fma(y, e * c, y);
+}
+
 // ---- GPU versions of the factorisation, the triangular solves and the gradient -----------------
 // Lane l of the group OWNS rows l, l + G, ... of the packed lower triangle (slots; N <= 64 gives
 // at most 64 / G of them).  A row's entries are only ever written by its owner, so
@@ -646,7 +658,7 @@ __device__ __forceinline__ int qp_chol_masked_rows(const QpWs& ws, int N, const 
         status |= KMPC_STATUS_PIVOT;
         d = floor_j;
       }
-      const double inv = rsqrt(d);
+      const double inv = rsqrt_pos(d);
       if (live) {
 #pragma unroll
         for (int sl = 0; sl < SLOTS; ++sl) {
